@@ -1,0 +1,69 @@
+// Shared device helpers for liblsk (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define LSK_VERSION 100
+
+// error codes of the C ABI: 0 ok, <0 argument error, >0 cudaError_t
+#define LSK_EARG  (-1)
+#define LSK_ESIZE (-2)
+#define LSK_EUNSUPPORTED (-3)
+
+namespace lsk {
+
+constexpr int BM = 64;          // rows of x (or of phases) per CTA tile == embedding panel height
+constexpr int BN = 64;          // columns per CTA tile
+constexpr int PANEL = 64;       // rows per panel of the embedded operand layout (must equal BM and BN)
+constexpr int KG_PER_STAGE = 8; // k-groups (of 4 doubles) per pipeline stage -> 16 KB per operand per stage
+constexpr int STAGES = 4;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;   // + one producer warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LSK_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LSK_DONE_%=;\n"
+        "bra LSK_WAIT_%=;\n"
+        "LSK_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine; SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col); fp64 tensor-core path (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void st_cs_f64x2(double* p, double a, double b) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_cs_f64(double* p, double a) {
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
+}
+
+}  // namespace lsk

@@ -1,0 +1,31 @@
+// Parameter block shared by the host API and the pairwise kernels.
+#pragma once
+#include <cstdint>
+
+#define LSK_MAX_FORMS 4
+#define LSK_MAX_VARS 4
+#define LSK_MAX_COEF 400
+#define LSK_MAX_ROWS 24
+
+// Epilogue kinds: how the class function is evaluated from the conjugation invariants.
+#define LSK_EPI_CHEB1   1   // rank 1:  sum_k coef[k] T_k(var0)                          (Clenshaw; SO(3), SU(2))
+#define LSK_EPI_STAIR2  2   // rank 2:  sum_b var1^b sum_a C[b][a] var0^a                (nested Horner; SO(5) fast path)
+#define LSK_EPI_ORBIT2  3   // rank 2:  sum_ab W[a][b] T_a(c1) T_b(c2), c1+c2=var0, c1*c2=var1 (Weyl-orbit form; robust path)
+#define LSK_EPI_SPARSE  4   // any:     sum_t coef[2t] prod_v var_v^{e_tv}, exponents packed 4 bits each in coef[2t+1]
+
+// One pairwise problem: `nforms` bilinear forms u_f(i,j) = sum_{k in groups [g0_f, g1_f)} A[i,k] B[j,k], then
+//   var_v = aff[v][0] + sum_f aff[v][1+f] * u_f,   out[i,j] = scale * P(var_0..var_{nvars-1}).
+// Passed by value as a kernel parameter, so the coefficient table lives in the constant bank and is read through
+// uniform loads (LDCU) - no device allocation, no host->device copy, no global state.
+struct LskEpilogue {
+    int32_t kind;
+    int32_t nforms;
+    int32_t nvars;
+    int32_t nterms;                        // CHEB1: #coefficients; STAIR2: #rows; ORBIT2: matrix size D; SPARSE: #terms
+    int32_t group_begin[LSK_MAX_FORMS];    // k-group (4 doubles) range of each form inside the embedded operands
+    int32_t group_end[LSK_MAX_FORMS];
+    int32_t row_len[LSK_MAX_ROWS];         // STAIR2: #coefficients in row b
+    double scale;
+    double aff[LSK_MAX_VARS][1 + LSK_MAX_FORMS];
+    double coef[LSK_MAX_COEF];
+};

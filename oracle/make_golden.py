@@ -1,0 +1,224 @@
+"""TEST INFRASTRUCTURE — generate the golden fixtures under tests/golden/ by running the REAL reference.
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+Every fixture stores the *inputs* (points, phases, weights, h_samples, spectral samples) and the reference's
+*outputs*, because CPU and CUDA generators differ: parity tests inject the same tensors into both sides
+(SURVEY.md §8c "same-tensor rule").  Files are small (float64 tensors, a few hundred KB in total).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+import warnings
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def main(only=None):
+    warnings.simplefilter("ignore")
+    ref_shim.import_reference()
+    from lie_stationary_kernels.spaces import (SO, SU, Stiefel, Grassmannian, OrientedGrassmannian, HyperbolicSpace,
+                                               SymmetricPositiveDefiniteMatrices)
+    from lie_stationary_kernels.spectral_kernel import (EigenbasisSumKernel, RandomPhaseKernel,
+                                                        RandomFourierFeatureKernel, RandomSpectralKernel)
+    from lie_stationary_kernels.spectral_measure import MaternSpectralMeasure, SqExpSpectralMeasure
+    from lie_stationary_kernels.prior_approximation import RandomPhaseApproximation, RandomFourierApproximation
+
+    os.makedirs(OUT, exist_ok=True)
+
+    def measure_of(spec):
+        if spec["kind"] == "matern":
+            return MaternSpectralMeasure(spec["dim"], spec["lengthscale"], spec["nu"], spec.get("variance", 1.0))
+        return SqExpSpectralMeasure(spec["dim"], spec["lengthscale"], spec.get("variance", 1.0))
+
+    def _detach(o):
+        if isinstance(o, torch.Tensor):
+            return o.detach().clone()
+        if isinstance(o, dict):
+            return {k: _detach(v) for k, v in o.items()}
+        return o
+
+    def save(name, obj):
+        torch.save(_detach(obj), os.path.join(OUT, name + ".pt"))
+        print("wrote %-40s %.1f KB" % (name, os.path.getsize(os.path.join(OUT, name + ".pt")) / 1024), flush=True)
+
+    def want(name):
+        return only is None or any(name.startswith(o) for o in only)
+
+    # ------------------------------------------------------------------ EigenbasisSumKernel on groups
+    eig_cases = [
+        ("eigsum_so3_heat_L20", SO, 3, 20, dict(kind="heat", dim=3, lengthscale=1.0), 96, 80),
+        ("eigsum_so3_matern_L100", SO, 3, 100, dict(kind="matern", dim=3, lengthscale=0.4, nu=0.5), 40, 40),
+        ("eigsum_so5_matern25_L100", SO, 5, 100, dict(kind="matern", dim=10, lengthscale=1.0, nu=2.5), 24, 24),
+        ("eigsum_so5_matern05_L100", SO, 5, 100, dict(kind="matern", dim=10, lengthscale=0.4, nu=0.5), 20, 20),
+        ("eigsum_so5_heat_L20", SO, 5, 20, dict(kind="heat", dim=10, lengthscale=0.8, variance=2.5), 40, 36),
+        ("eigsum_so7_heat_L20", SO, 7, 20, dict(kind="heat", dim=21, lengthscale=1.0), 20, 20),
+        ("eigsum_su2_heat_L20", SU, 2, 20, dict(kind="heat", dim=3, lengthscale=1.0), 40, 40),
+        ("eigsum_su3_matern_L20", SU, 3, 20, dict(kind="matern", dim=8, lengthscale=1.0, nu=1.5), 32, 32),
+        ("eigsum_su4_heat_L20", SU, 4, 20, dict(kind="heat", dim=15, lengthscale=1.0), 40, 36),
+        ("eigsum_su5_heat_L10", SU, 5, 10, dict(kind="heat", dim=24, lengthscale=1.0), 16, 16),
+        ("eigsum_so4_heat_L20", SO, 4, 20, dict(kind="heat", dim=6, lengthscale=1.0), 24, 24),
+        ("eigsum_so6_heat_L20", SO, 6, 20, dict(kind="heat", dim=15, lengthscale=1.0), 20, 20),
+    ]
+    for name, cls, n, order, mspec, nx, ny in eig_cases:
+        if not want(name):
+            continue
+        t0 = time.time()
+        torch.manual_seed(1234)
+        space = cls(n, order=order)
+        kern = EigenbasisSumKernel(measure_of(mspec), space)
+        kern.eval()
+        x, y = space.rand(nx), space.rand(ny)
+        y[:3] = x[:3]                                 # exercise the diagonal (identity class)
+        with torch.no_grad():
+            k_norm = kern(x, y)
+            k_raw = kern(x, y, normalize=False)
+            k_xx = kern(x[:8])
+        save(name, dict(group=cls.__name__, n=n, order=order, measure=mspec, x=x, y=y,
+                        normalizer=kern.normalizer.detach().clone(), k_norm=k_norm, k_raw=k_raw, k_xx=k_xx,
+                        irreps=[(e.index, e.dimension, e.lb_eigenvalue) for e in space.lb_eigenspaces]))
+        print("   %.1fs" % (time.time() - t0), flush=True)
+
+    # ------------------------------------------------------------------ torus representatives / characters (lie_groups.py tests)
+    if want("chars"):
+        torch.manual_seed(7)
+        rec = {}
+        for cls, n in ((SO, 3), (SO, 5), (SO, 7), (SU, 2), (SU, 3), (SU, 4)):
+            space = cls(n, order=10)
+            x = space.rand(12)
+            gam = space.torus_representative(x)
+            vals = torch.stack([e.phase_function.chi(gam) for e in space.lb_eigenspaces])
+            rec["%s%d" % (cls.__name__, n)] = dict(x=x, chi=vals, sigs=[e.index for e in space.lb_eigenspaces])
+        save("chars_small", rec)
+
+    # ------------------------------------------------------------------ space.rand (inputs = the Gaussian draws)
+    if want("rand"):
+        rec = {}
+        for cls, n, num in ((SO, 3, 64), (SO, 5, 64), (SO, 8, 32), (SU, 2, 64), (SU, 4, 48), (SU, 6, 16)):
+            space = cls(n, order=0)
+            torch.manual_seed(99)
+            q = space.rand(num)
+            torch.manual_seed(99)
+            if (cls is SO and n == 3) or (cls is SU and n == 2):
+                gauss = torch.randn((num, 4), dtype=torch.float64)
+            else:
+                gauss = torch.randn((num, n, n), dtype=torch.float64 if cls is SO else torch.complex128)
+            rec["%s%d" % (cls.__name__, n)] = dict(gauss=gauss, q=q)
+        hyp = HyperbolicSpace(3, order=4)
+        torch.manual_seed(99)
+        pts = hyp.rand(32)
+        torch.manual_seed(99)
+        g = torch.randn(32, 3, dtype=torch.float64)
+        u = torch.rand(32, dtype=torch.float64)
+        rec["H3"] = dict(gauss=g, unif=u, x=pts)
+        spd = SymmetricPositiveDefiniteMatrices(3, order=4)
+        torch.manual_seed(99)
+        pts = spd.rand(32)
+        torch.manual_seed(99)
+        g = torch.randn(32, 3, 3, dtype=torch.float64)
+        rec["SPD3"] = dict(gauss=g, x=pts)
+        save("rand_draws", rec)
+
+    # ------------------------------------------------------------------ homogeneous spaces: lift, embedding, Gram, sampler
+    hom_cases = [
+        ("homog_stiefel53", Stiefel, (5, 3), dict(order=10, average_order=30), dict(kind="matern", dim=9, lengthscale=1.0, nu=2.5), 20, 12),
+        ("homog_stiefel52_heat", Stiefel, (5, 2), dict(order=10, average_order=12), dict(kind="heat", dim=7, lengthscale=0.7), 12, 8),
+        ("homog_grassmannian52", Grassmannian, (5, 2), dict(order=10, average_order=20), dict(kind="heat", dim=6, lengthscale=1.0), 12, 8),
+        ("homog_orgrassmannian52", OrientedGrassmannian, (5, 2), dict(order=10, average_order=16), dict(kind="heat", dim=6, lengthscale=1.0), 12, 8),
+        ("homog_stiefel32", Stiefel, (3, 2), dict(order=10, average_order=10), dict(kind="heat", dim=3, lengthscale=1.0), 12, 8),
+    ]
+    for name, cls, nm, kw, mspec, nx, nph in hom_cases:
+        if not want(name):
+            continue
+        t0 = time.time()
+        torch.manual_seed(4321)
+        space = cls(*nm, **kw)
+        meas = measure_of(mspec)
+        kern = RandomPhaseKernel(meas, space, phase_order=nph)
+        kern.eval()
+        x = space.rand(nx).contiguous()
+        y = space.rand(nx - 3).contiguous()
+        with torch.no_grad():
+            emb = kern.make_embedding(x)
+            gram = kern(x, y).evaluate()
+            gram_raw = kern(x, y, normalize=False).evaluate()
+            esum = EigenbasisSumKernel(meas, space)
+            esum.eval()
+            k_es = esum(x, y)
+            sampler = RandomPhaseApproximation(esum, phase_order=nph)
+            sample = sampler(x)
+            samp_emb = sampler.make_embedding(x)
+        save(name, dict(cls=cls.__name__, nm=nm, kw=kw, measure=mspec, x=x, y=y, h_samples=space.h_samples,
+                        phases=kern.phases.contiguous(), normalizer=kern.normalizer.detach().clone(), embedding=emb,
+                        gram=gram, gram_raw=gram_raw,
+                        lift_x=space.M_to_G(x), es_normalizer=esum.normalizer.detach().clone(), k_es=k_es,
+                        s_phases=sampler.phases.contiguous(), s_weights=sampler.weights, sample=sample, s_embedding=samp_emb))
+        print("   %.1fs" % (time.time() - t0), flush=True)
+
+    # ------------------------------------------------------------------ RandomPhaseKernel / sampler on a group manifold
+    for name, cls, n, order, mspec, nx, nph in [
+        ("rpk_so3", SO, 3, 12, dict(kind="heat", dim=3, lengthscale=1.0), 24, 16),
+        ("rpk_so5", SO, 5, 10, dict(kind="matern", dim=10, lengthscale=1.0, nu=2.5), 16, 12),
+        ("rpk_su3", SU, 3, 10, dict(kind="heat", dim=8, lengthscale=1.0), 16, 12),
+    ]:
+        if not want(name):
+            continue
+        torch.manual_seed(2468)
+        space = cls(n, order=order)
+        meas = measure_of(mspec)
+        kern = RandomPhaseKernel(meas, space, phase_order=nph)
+        kern.eval()
+        x, y = space.rand(nx), space.rand(nx - 5)
+        with torch.no_grad():
+            emb = kern.make_embedding(x)
+            gram = kern(x, y).evaluate()
+            esum = EigenbasisSumKernel(meas, space)
+            esum.eval()
+            sampler = RandomPhaseApproximation(esum, phase_order=nph)
+            sample = sampler(x)
+        save(name, dict(group=cls.__name__, n=n, order=order, measure=mspec, x=x, y=y, phases=kern.phases,
+                        normalizer=kern.normalizer.detach().clone(), embedding=emb, gram=gram,
+                        es_normalizer=esum.normalizer.detach().clone(), s_phases=sampler.phases,
+                        s_weights=sampler.weights, sample=sample))
+
+    # ------------------------------------------------------------------ non-compact: H^n and SPD(n)
+    for name, cls, n, order, mspec, nx in [
+        ("rff_h3_matern", HyperbolicSpace, 3, 96, dict(kind="matern", dim=3, lengthscale=1.0, nu=2.5), 40),
+        ("rff_h3_heat", HyperbolicSpace, 3, 96, dict(kind="heat", dim=3, lengthscale=1.0), 40),
+        ("rff_h2_heat", HyperbolicSpace, 2, 64, dict(kind="heat", dim=2, lengthscale=0.8), 24),
+        ("rff_h5_matern", HyperbolicSpace, 5, 64, dict(kind="matern", dim=5, lengthscale=1.0, nu=1.5), 24),
+        ("rff_spd3_matern", SymmetricPositiveDefiniteMatrices, 3, 96, dict(kind="matern", dim=6, lengthscale=1.0, nu=2.5), 40),
+        ("rff_spd3_heat", SymmetricPositiveDefiniteMatrices, 3, 96, dict(kind="heat", dim=6, lengthscale=1.0), 40),
+        ("rff_spd2_heat", SymmetricPositiveDefiniteMatrices, 2, 64, dict(kind="heat", dim=3, lengthscale=1.0), 24),
+        ("rff_spd4_heat", SymmetricPositiveDefiniteMatrices, 4, 48, dict(kind="heat", dim=10, lengthscale=1.5), 16),
+    ]:
+        if not want(name):
+            continue
+        torch.manual_seed(1357)
+        space = cls(n, order=order)
+        meas = measure_of(mspec)
+        kern = RandomFourierFeatureKernel(meas, space)
+        kern.eval()
+        x, y = space.rand(nx), space.rand(nx - 7)
+        with torch.no_grad():
+            feats = space.lb_eigenspaces(space.to_group(x))
+            gram = kern(x, y).evaluate()
+            sampler = RandomFourierApproximation(kern)
+            sample = sampler(x)
+            cov = sampler._cov(x, y)
+        save(name, dict(cls=cls.__name__, n=n, order=order, measure=mspec, x=x, y=y,
+                        lmd=space.lb_eigenspaces.exp.lmd, shift=space.lb_eigenspaces.exp.shift,
+                        coeff=space.lb_eigenspaces.coeff, normalizer=kern.normalizer.detach().clone(),
+                        features=feats, gram=gram, w_re=sampler.weights_real, w_im=sampler.weights_imag,
+                        sample=sample, cov=cov))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or None)
