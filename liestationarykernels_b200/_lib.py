@@ -1,0 +1,109 @@
+"""ctypes binding of liblsk.so — the C-ABI boundary (include/lsk.h).
+
+There is no CPU fallback: if the shared object is missing, or no CUDA device is present, every compute entry
+point raises.  The library is loaded from this directory only (built in-tree by `build.py`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblsk.so")
+
+MAX_FORMS = 4
+MAX_VARS = 4
+MAX_COEF = 400
+MAX_ROWS = 24
+
+EPI_CHEB1, EPI_STAIR2, EPI_ORBIT2, EPI_SPARSE = 1, 2, 3, 4
+
+
+class LskEpilogue(ctypes.Structure):
+    """Mirror of `struct LskEpilogue` (include/lsk.h)."""
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("nforms", ctypes.c_int32),
+        ("nvars", ctypes.c_int32),
+        ("nterms", ctypes.c_int32),
+        ("group_begin", ctypes.c_int32 * MAX_FORMS),
+        ("group_end", ctypes.c_int32 * MAX_FORMS),
+        ("row_len", ctypes.c_int32 * MAX_ROWS),
+        ("scale", ctypes.c_double),
+        ("aff", (ctypes.c_double * (1 + MAX_FORMS)) * MAX_VARS),
+        ("coef", ctypes.c_double * MAX_COEF),
+    ]
+
+
+class LskError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_PROTOTYPES = {
+    "lsk_version": (ctypes.c_int, []),
+    "lsk_embed_buffer_doubles": (ctypes.c_longlong, [ctypes.c_longlong, ctypes.c_int]),
+    "lsk_embed_points": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                        ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "lsk_pairwise_poly": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
+                                         ctypes.POINTER(LskEpilogue), ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
+}
+
+
+def exported_symbols():
+    return sorted(_PROTOTYPES)
+
+
+def load():
+    """Loads liblsk.so (once). Raises LskError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LskError("liblsk.so not found at %s - run `python -m liestationarykernels_b200.build` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise LskError("liestationarykernels_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def check(code: int, what: str):
+    if code == 0:
+        return
+    if code < 0:
+        names = {-1: "invalid argument", -2: "size out of range", -3: "unsupported configuration"}
+        raise LskError("%s: %s (code %d)" % (what, names.get(code, "argument error"), code))
+    raise LskError("%s: CUDA error %d" % (what, code))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: torch.Tensor):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+_launch_count = 0
+
+
+def count_launch(n=1):
+    """bench.py reports `gpu_launches`: every kernel launch made through this binding is counted here."""
+    global _launch_count
+    _launch_count += n
+
+
+def launches():
+    return _launch_count

@@ -1,0 +1,373 @@
+"""Host-side plans for class functions on compact Lie groups: which per-point embeddings the CUDA kernels need,
+how the bilinear forms map to polynomial variables, and the integer matrix that turns spectral weights into
+the coefficient table of the fused epilogue (`struct LskEpilogue`, include/lsk.h).
+
+Everything here is exact integer/rational arithmetic done once per (group, n, order); per call only
+`coef = M^T (a_lambda * d_lambda)` (a few hundred flops) runs on the host.
+
+Reference behaviour covered: `torus_representative` + `chi` + the weighted sum of `EigenbasisSumKernel.forward`
+(`spaces/so.py:136-168,288-293`, `spaces/su.py:91-92,175-179`, `spectral_kernel.py:45-54`).
+"""
+from __future__ import annotations
+
+import math
+from fractions import Fraction
+from functools import lru_cache
+
+import numpy as np
+
+from . import characters as ch
+from . import invariants as inv
+from ._lib import (EPI_CHEB1, EPI_ORBIT2, EPI_SPARSE, EPI_STAIR2, MAX_COEF, MAX_FORMS, MAX_ROWS, MAX_VARS,
+                   LskEpilogue)
+
+
+def _binom(n, k):
+    return math.comb(n, k)
+
+
+class GroupPlan:
+    """Embedding layout + polynomial tables for one (family, n, order)."""
+
+    def __init__(self, family: str, n: int, order: int):
+        self.family, self.n, self.order = family, n, order
+        kept, dropped = ch.truncated_irreps(family, n, order) if order else ([], [])
+        self.irreps = kept
+        self.dropped = dropped
+        self.is_complex = family == "SU"
+        self._build_forms()
+        if order:
+            self._build_polynomials()
+
+    # ------------------------------------------------------------------ embeddings / bilinear forms
+    def _build_forms(self):
+        n = self.n
+        segs_a, segs_b = [], []        # (wedge, part)
+        if self.family == "SO":
+            if n % 2 == 0:
+                raise NotImplementedError(
+                    "SO(%d): even special orthogonal groups need the Pfaffian sign invariant, which this build does "
+                    "not provide yet (SURVEY.md 7.3); supported: SO(3), SO(5), SO(7)" % n)
+            rank = n // 2
+            if rank > 3:
+                raise NotImplementedError("SO(%d): compound matrices beyond Lambda^3 are not implemented" % n)
+            for k in range(1, rank + 1):
+                segs_a.append((k, 0))
+                segs_b.append((k, 0))
+            self.real_vars = rank
+        else:
+            if n > 5:
+                raise NotImplementedError("SU(%d): needs more than %d real invariants" % (n, MAX_VARS))
+            # e_k for k <= n/2; e_{n-k} = conj(e_k); e_{n/2} is real for even n
+            half = n // 2
+            for k in range(1, half + 1):
+                real_only = (n % 2 == 0 and k == half)
+                segs_a.append((k, 1))
+                segs_b.append((k, 2))
+                if not real_only:
+                    segs_a.append((k, 1))
+                    segs_b.append((k, 3))
+            self.real_vars = len(segs_a)
+        assert len(segs_a) <= MAX_FORMS
+        self.segments_a, self.segments_b = segs_a, segs_b
+        begin, g = [], 0
+        for (k, part) in segs_a:
+            begin.append(g)
+            length = _binom(n, k) ** 2 * (2 if self.is_complex else 1)
+            g += (length + 3) // 4
+        self.group_begin = begin
+        self.kg_total = g
+        self.group_end = begin[1:] + [g]
+        self.nforms = len(segs_a)
+
+    # ------------------------------------------------------------------ class polynomials
+    def _build_polynomials(self):
+        sigs = [r[0] for r in self.irreps]
+        n = self.n
+        if self.family == "SO":
+            rank = n // 2
+            if rank == 1:
+                self.kind = "cheb1"
+                # chi_l = sum_mu m(mu) orb_mu,  orb_mu = 2 T_mu(c) (mu > 0), 1 (mu = 0);  c = (tr g - 1) / 2
+                deg = max(s[0] for s in sigs)
+                M = np.zeros((len(sigs), deg + 1))
+                for l, s in enumerate(sigs):
+                    for mu, m in ch.dominant_weight_multiplicities("B", tuple(s)).items():
+                        M[l, mu[0]] += m * (2 if mu[0] else 1)
+                self.M = M
+                self.aff = [[-0.5, 0.5]]
+                return
+            monos, mat = inv.character_matrix("SO", n, sigs)
+            self.monos = monos
+            self.M = np.array(mat, dtype=np.float64)
+            assert np.all(np.abs(self.M) < 2.0 ** 53)
+            self.aff = _so_odd_affine(n)
+            if rank == 2:
+                self.kind = "rank2"
+                self._build_stair(monos)
+                self._build_orbit(sigs)
+            else:
+                self.kind = "sparse"
+                self.sparse_expo = monos
+            return
+        # SU(n)
+        if n == 2:
+            self.kind = "cheb1"
+            deg = max(s[0] for s in sigs)
+            M = np.zeros((len(sigs), deg + 1))
+            for l, s in enumerate(sigs):
+                for w, m in ch.character_weights("SU", 2, s).items():
+                    M[l, abs(w[0] - w[1])] += m          # e^{i(w0-w1)theta}; the +-pair sums to 2 T_k(cos theta)
+            self.M = M
+            self.aff = [[0.0, 0.5]]                        # cos(theta) = Re tr(g) / 2
+            return
+        self.kind = "sparse"
+        monos, mat = _su_real_character_matrix(n, sigs)
+        self.sparse_expo = monos
+        self.M = np.array(mat, dtype=np.float64)
+        assert np.all(np.abs(self.M) < 2.0 ** 53)
+        self.aff = [[0.0] + [1.0 if f == v else 0.0 for f in range(self.nforms)] for v in range(self.nforms)]
+
+    def _build_stair(self, monos):
+        rows = {}
+        for (a, b) in monos:
+            rows[b] = max(rows.get(b, -1), a)
+        nrows = max(rows) + 1
+        self.stair_rows = [rows.get(b, 0) + 1 for b in range(nrows)]
+        # evaluation order: highest b first, inside a row highest a first
+        index = {m: i for i, m in enumerate(monos)}
+        order = []
+        for b in range(nrows - 1, -1, -1):
+            for a in range(self.stair_rows[b] - 1, -1, -1):
+                order.append(index.get((a, b), -1))
+        self.stair_order = np.array(order)
+        self.stair_ok = nrows <= MAX_ROWS and len(order) <= MAX_COEF
+
+    def _build_orbit(self, sigs):
+        # W[mu] = sum_l w_l m_l(mu);  full symmetric Chebyshev-product matrix (see lsk_pairwise.cu epi_orbit2)
+        dom = sorted(set().union(*[set(ch.dominant_weight_multiplicities("B", tuple(s))) for s in sigs]))
+        self.orbit_weights = dom
+        D = max(mu[0] for mu in dom) + 1
+        self.orbit_D = D
+        Mo = np.zeros((len(sigs), len(dom)))
+        for l, s in enumerate(sigs):
+            for mu, m in ch.dominant_weight_multiplicities("B", tuple(s)).items():
+                Mo[l, dom.index(mu)] = m
+        self.M_orbit = Mo
+        fac = []
+        for (a, b) in dom:
+            fac.append(1.0 if a == 0 else (2.0 if b == 0 else 4.0))
+        self.orbit_fac = np.array(fac)
+
+    # ------------------------------------------------------------------ epilogue for given irrep weights
+    def _base_epilogue(self) -> LskEpilogue:
+        ep = LskEpilogue()
+        ep.nforms = self.nforms
+        for f in range(self.nforms):
+            ep.group_begin[f] = self.group_begin[f]
+            ep.group_end[f] = self.group_end[f]
+        ep.nvars = len(self.aff)
+        for v, row in enumerate(self.aff):
+            for i, val in enumerate(row):
+                ep.aff[v][i] = float(val)
+        ep.scale = 1.0
+        return ep
+
+    def epilogue(self, weights: np.ndarray, scale: float, form: str = "auto") -> LskEpilogue:
+        """weights[l] multiplies chi_l (typically a_l * d_l).  form in {'auto', 'fast', 'robust'} (rank 2 only)."""
+        w = np.asarray(weights, dtype=np.float64)
+        ep = self._base_epilogue()
+        ep.scale = float(scale)
+        if self.kind == "cheb1":
+            coef = _dot_long(w, self.M)
+            if len(coef) > MAX_COEF:
+                raise ValueError("order too large for the rank-1 epilogue (%d > %d)" % (len(coef), MAX_COEF))
+            ep.kind, ep.nterms = EPI_CHEB1, len(coef)
+            for i, c in enumerate(coef):
+                ep.coef[i] = c
+            return ep
+        if self.kind == "rank2":
+            use_fast = form == "fast" or (form == "auto" and self.stair_ok and self.fast_form_is_safe(w))
+            if use_fast:
+                if not self.stair_ok:
+                    raise ValueError("staircase table too large for the fast form")
+                coef = _dot_long(w, self.M)
+                ep.kind, ep.nterms = EPI_STAIR2, len(self.stair_rows)
+                for b, ln in enumerate(self.stair_rows):
+                    ep.row_len[b] = ln
+                for i, j in enumerate(self.stair_order):
+                    ep.coef[i] = coef[j] if j >= 0 else 0.0
+                return ep
+            D = self.orbit_D
+            if D > 20:
+                raise ValueError("order too large for the Weyl-orbit epilogue (max exponent %d > 19)" % (D - 1))
+            Dp = 8 if D <= 8 else 12 if D <= 12 else 16 if D <= 16 else 20
+            W = _dot_long(w, self.M_orbit) * self.orbit_fac
+            ep.kind, ep.nterms = EPI_ORBIT2, D
+            full = np.zeros((Dp, Dp))
+            for (a, b), val in zip(self.orbit_weights, W):
+                full[a, b] = val
+                full[b, a] = val
+            for a in range(D):
+                for b in range(Dp):
+                    ep.coef[a * Dp + b] = full[a, b]
+            return ep
+        # sparse
+        coef = _dot_long(w, self.M)
+        keep = [(c, e) for c, e in zip(coef, self.sparse_expo) if c != 0.0]
+        if 2 * len(keep) > MAX_COEF:
+            raise ValueError("too many polynomial terms for the sparse epilogue (%d > %d)" % (len(keep), MAX_COEF // 2))
+        ep.kind, ep.nterms = EPI_SPARSE, len(keep)
+        for t, (c, e) in enumerate(keep):
+            ep.coef[2 * t] = c
+            packed = 0
+            for i, ei in enumerate(e):
+                assert 0 <= ei < 256
+                packed |= int(ei) << (8 * i)
+            ep.coef[2 * t + 1] = np.array([packed], dtype=np.uint64).view(np.float64)[0]
+        return ep
+
+    # ------------------------------------------------------------------ fast-form safety check (rank 2)
+    def _probe(self):
+        if getattr(self, "_probe_cache", None) is not None:
+            return self._probe_cache
+        rng = np.random.default_rng(12345)
+        th = rng.uniform(0, math.pi, size=(2, 4096))
+        th[:, :64] *= 0.05                                   # near the identity class, where the kernel peaks
+        c1, c2 = np.cos(th[0]), np.cos(th[1])
+        s1, s2 = c1 + c2, c1 * c2
+        D = self.orbit_D
+        T1 = np.cos(np.arange(D)[:, None] * th[0][None, :])
+        T2 = np.cos(np.arange(D)[:, None] * th[1][None, :])
+        orb = np.stack([(T1[a] * T2[b] + T1[b] * T2[a]) * (0.5 if a == b else 1.0) for (a, b) in self.orbit_weights])
+        self._probe_cache = (s1, s2, orb)
+        return self._probe_cache
+
+    def fast_form_is_safe(self, w: np.ndarray, tol: float = 2e-13) -> bool:
+        """Evaluates the monomial (fast) and Weyl-orbit (robust) forms in float64 on 4096 probe classes and accepts
+        the fast one only when they agree to `tol` relative to the local kernel value — the monomial basis loses
+        digits for slowly decaying spectra (Matern-1/2, l=0.4 gives 5e-11)."""
+        s1, s2, orb = self._probe()
+        robust = (_dot_long(w, self.M_orbit) * self.orbit_fac) @ orb
+        coef = _dot_long(w, self.M)
+        fast = np.zeros_like(s1)
+        pos = 0
+        table = [coef[j] if j >= 0 else 0.0 for j in self.stair_order]
+        for b in range(len(self.stair_rows) - 1, -1, -1):
+            ln = self.stair_rows[b]
+            inner = np.full_like(s1, table[pos])
+            for a in range(1, ln):
+                inner = inner * s1 + table[pos + a]
+            pos += ln
+            fast = fast * s2 + inner
+        denom = np.maximum(np.abs(robust), 1e-300)
+        return bool(np.max(np.abs(fast - robust) / denom) < tol)
+
+
+def _dot_long(w: np.ndarray, M: np.ndarray) -> np.ndarray:
+    """w @ M accumulated in extended precision: the integer entries of M reach 1e7 and alternate in sign."""
+    return np.asarray((w.astype(np.longdouble)[None, :] @ M.astype(np.longdouble))[0], dtype=np.float64)
+
+
+def _so_odd_affine(n: int):
+    """Rows [const, coef of e_1, ..., coef of e_r]: s_k(cos theta) as an affine function of e_1..e_r of g in SO(n).
+    det(zI - g) = (z - 1) prod_i (z^2 - 2 c_i z + 1) = sum_k (-1)^k e_k z^{n-k}."""
+    r = n // 2
+
+    def pmul(a, b):
+        out = [Fraction(0)] * (len(a) + len(b) - 1)
+        for i, x in enumerate(a):
+            for j, y in enumerate(b):
+                out[i + j] += x * y
+        return out
+
+    # polys in z, low -> high;  basis_j(z) = (z - 1) (-2z)^j (z^2 + 1)^(r - j), multiplied by s_j (s_0 = 1)
+    basis = []
+    for j in range(r + 1):
+        p = [Fraction(1)]
+        for _ in range(j):
+            p = pmul(p, [Fraction(0), Fraction(-2)])
+        for _ in range(r - j):
+            p = pmul(p, [Fraction(1), Fraction(0), Fraction(1)])
+        basis.append(pmul(p, [Fraction(-1), Fraction(1)]))
+    # e_k = (-1)^k * coefficient of z^(n-k):   e_k = T[k][0] + sum_j T[k][j] s_j
+    T = [[(-1) ** k * (basis[j][n - k] if n - k < len(basis[j]) else Fraction(0)) for j in range(r + 1)] for k in range(r + 1)]
+    # solve for s_1..s_r from e_1..e_r (triangular: e_k involves s_j for j <= k)
+    rows = []
+    sol = {0: ([Fraction(1)] + [Fraction(0)] * r)}            # s_0 = 1 as affine function of (1, e_1..e_r)
+    for k in range(1, r + 1):
+        # e_k = sum_{j<=k} T[k][j] s_j  ->  s_k = (e_k - sum_{j<k} T[k][j] s_j) / T[k][k]
+        acc = [Fraction(0)] * (r + 1)
+        acc[k] = Fraction(1)
+        for j in range(k):
+            for i in range(r + 1):
+                acc[i] -= T[k][j] * sol[j][i]
+        assert T[k][k] != 0 and all(T[k][j] == 0 for j in range(k + 1, r + 1))
+        sol[k] = [a / T[k][k] for a in acc]
+        rows.append([float(v) for v in sol[k]])
+    return rows
+
+
+def _su_real_character_matrix(n: int, sigs):
+    """Characters of SU(n) as real polynomials in the real invariants
+       (Re e_1, Im e_1, Re e_2, Im e_2, ...) [and e_{n/2} real for even n] - only the real part, which is all the
+       kernels use (`spectral_kernel.py:50` takes `.real`)."""
+    half = n // 2
+    names = []           # variable index of (k, 're'/'im')
+    for k in range(1, half + 1):
+        names.append((k, "re"))
+        if not (n % 2 == 0 and k == half):
+            names.append((k, "im"))
+    nv = len(names)
+    vid = {nm: i for i, nm in enumerate(names)}
+
+    def unit(i):
+        return tuple(1 if j == i else 0 for j in range(nv))
+
+    zero = tuple([0] * nv)
+
+    def e_complex(k):
+        """e_k as (re_poly, im_poly) in the real variables."""
+        kk = k if k <= half else n - k
+        re = {unit(vid[(kk, "re")]): 1}
+        im = {unit(vid[(kk, "im")]): (1 if k <= half else -1)} if (kk, "im") in vid else {}
+        return re, im
+
+    def cmul(a, b):
+        re = inv.p_add(inv.p_mul(a[0], b[0]), inv.p_mul(a[1], b[1]), -1)
+        im = inv.p_add(inv.p_mul(a[0], b[1]), inv.p_mul(a[1], b[0]))
+        return re, im
+
+    pow_cache = {}
+
+    def cpow(k, p):
+        if (k, p) not in pow_cache:
+            if p == 0:
+                pow_cache[(k, p)] = ({zero: 1}, {})
+            else:
+                pow_cache[(k, p)] = cmul(cpow(k, p - 1), e_complex(k))
+        return pow_cache[(k, p)]
+
+    polys = []
+    for s in sigs:
+        cp = inv.su_character_poly(n, tuple(s))
+        real = {}
+        for expo, c in cp.items():
+            term = ({zero: 1}, {})
+            for k, p in enumerate(expo, start=1):
+                if p:
+                    term = cmul(term, cpow(k, p))
+            real = inv.p_add(real, term[0], c)
+        polys.append(real)
+    monos = sorted(set().union(*[set(p) for p in polys]))
+    index = {m: i for i, m in enumerate(monos)}
+    mat = [[0] * len(monos) for _ in polys]
+    for l, p in enumerate(polys):
+        for m, c in p.items():
+            mat[l][index[m]] = c
+    return monos, mat
+
+
+@lru_cache(maxsize=None)
+def group_plan(family: str, n: int, order: int) -> GroupPlan:
+    return GroupPlan(family, n, order)

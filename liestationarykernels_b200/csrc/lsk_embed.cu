@@ -1,0 +1,146 @@
+// Per-point embeddings: the O(N) prologue of the pairwise kernels.
+//
+// For g = x y^{-1} in SO(n) / SU(n) the coefficients of the characteristic polynomial are bilinear in the
+// compound matrices of x and y (Cauchy-Binet):  e_k(x y^T) = < Lambda^k x , Lambda^k y >_F  (with a conjugate on y
+// for SU(n)).  This kernel writes, for every point, the concatenation of the requested compound matrices
+// (k = 1: the matrix itself) into the panel-major operand layout of lsk_pairwise.cu:
+//     out[panel][k-group][row in panel (64)][4]      (doubles; rows beyond `num` and pad columns are zero)
+// It replaces the reference's `inv` + `cartesian_prod` + `bmm` operand preparation (space.py:62-78).
+#include "lsk_common.cuh"
+
+namespace lsk {
+
+struct EmbedSpec {
+    int nseg;
+    int wedge[4];        // 1, 2 or 3
+    int part[4];         // 0: real matrix;  1: complex (re, im);  2: complex (re, im) [B side, real form];
+                         // 3: complex (-im, re) [B side, imaginary form]
+    int group_begin[4];  // first k-group of the segment
+    int length[4];       // number of doubles in the segment (before padding to a multiple of 4)
+};
+
+__device__ __forceinline__ int binom(int n, int k) {
+    int r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return r;
+}
+
+// lexicographic rank -> increasing index tuple of size k (k <= 3) out of n
+__device__ __forceinline__ void unrank(int idx, int n, int k, int (&t)[3]) {
+    int start = 0;
+    for (int pos = 0; pos < k; ++pos) {
+        for (int v = start; v < n; ++v) {
+            const int cnt = binom(n - v - 1, k - pos - 1);
+            if (idx < cnt) { t[pos] = v; start = v + 1; break; }
+            idx -= cnt;
+        }
+    }
+}
+
+template <bool CPLX>
+__device__ __forceinline__ void load(const double* x, int n, int r, int c, double& re, double& im) {
+    if (CPLX) { re = x[2 * (r * n + c)]; im = x[2 * (r * n + c) + 1]; }
+    else { re = x[r * n + c]; im = 0.0; }
+}
+
+__device__ __forceinline__ void cmul(double ar, double ai, double br, double bi, double& cr, double& ci) {
+    cr = ar * br - ai * bi;
+    ci = ar * bi + ai * br;
+}
+
+template <bool CPLX>
+__device__ void minor(const double* x, int n, int k, const int (&I)[3], const int (&J)[3], double& re, double& im) {
+    if (k == 1) { load<CPLX>(x, n, I[0], J[0], re, im); return; }
+    if (k == 2) {
+        double ar, ai, br, bi, cr, ci, dr, di, p1r, p1i, p2r, p2i;
+        load<CPLX>(x, n, I[0], J[0], ar, ai); load<CPLX>(x, n, I[1], J[1], dr, di);
+        load<CPLX>(x, n, I[0], J[1], br, bi); load<CPLX>(x, n, I[1], J[0], cr, ci);
+        cmul(ar, ai, dr, di, p1r, p1i); cmul(br, bi, cr, ci, p2r, p2i);
+        re = p1r - p2r; im = p1i - p2i;
+        return;
+    }
+    // k == 3: cofactor expansion along the first row
+    double m[3][3][2];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) load<CPLX>(x, n, I[a], J[b], m[a][b][0], m[a][b][1]);
+    re = 0.0; im = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;     // cyclic: sign is always +
+        double p1r, p1i, p2r, p2i, tr, ti;
+        cmul(m[1][c1][0], m[1][c1][1], m[2][c2][0], m[2][c2][1], p1r, p1i);
+        cmul(m[1][c2][0], m[1][c2][1], m[2][c1][0], m[2][c1][1], p2r, p2i);
+        cmul(m[0][c][0], m[0][c][1], p1r - p2r, p1i - p2i, tr, ti);
+        re += tr; im += ti;
+    }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, EmbedSpec spec, double* __restrict__ out) {
+    const long long total = ((num + PANEL - 1) / PANEL) * (long long)kg_total * (PANEL * 4);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx & 3);
+        const int r = (int)((idx >> 2) & (PANEL - 1));
+        const long long gp = idx / (PANEL * 4);
+        const int g = (int)(gp % kg_total);
+        const long long row = (gp / kg_total) * PANEL + r;
+        double val = 0.0;
+        if (row < num) {
+            int seg = 0;
+            for (int s = 1; s < spec.nseg; ++s) if (g >= spec.group_begin[s]) seg = s;
+            const int e = (g - spec.group_begin[seg]) * 4 + j;
+            if (e < spec.length[seg]) {
+                const int k = spec.wedge[seg], part = spec.part[seg];
+                const int C = binom(n, k);
+                const int el = CPLX ? (e >> 1) : e;
+                int I[3] = {0, 0, 0}, J[3] = {0, 0, 0};
+                unrank(el / C, n, k, I);
+                unrank(el % C, n, k, J);
+                double re, im;
+                minor<CPLX>(x + row * (long long)(CPLX ? 2 : 1) * n * n, n, k, I, J, re, im);
+                if (!CPLX) val = re;
+                else if (part == 3) val = (e & 1) ? re : -im;
+                else val = (e & 1) ? im : re;
+            }
+        }
+        out[idx] = val;
+    }
+}
+
+}  // namespace lsk
+
+extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_complex, int nseg,
+                                const int* wedge, const int* part, const int* group_begin, int kg_total,
+                                void* out, void* stream) {
+    using namespace lsk;
+    if (!x || !out || !wedge || !part || !group_begin) return LSK_EARG;
+    if (num < 0 || n < 1 || n > 8 || nseg < 1 || nseg > 4 || kg_total < 1) return LSK_ESIZE;
+    if (num == 0) return 0;
+    EmbedSpec spec;
+    spec.nseg = nseg;
+    for (int s = 0; s < 4; ++s) { spec.wedge[s] = 1; spec.part[s] = 0; spec.group_begin[s] = 0; spec.length[s] = 0; }
+    for (int s = 0; s < nseg; ++s) {
+        if (wedge[s] < 1 || wedge[s] > 3 || wedge[s] > n) return LSK_EARG;
+        if (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0)) return LSK_EARG;
+        int c = 1;
+        for (int i = 1; i <= wedge[s]; ++i) c = c * (n - wedge[s] + i) / i;
+        spec.wedge[s] = wedge[s]; spec.part[s] = part[s]; spec.group_begin[s] = group_begin[s];
+        spec.length[s] = c * c * (is_complex ? 2 : 1);
+        const int end = group_begin[s] + (spec.length[s] + 3) / 4;
+        if (group_begin[s] < 0 || end > kg_total) return LSK_ESIZE;
+        if (s > 0 && group_begin[s] < spec.group_begin[s - 1] + (spec.length[s - 1] + 3) / 4) return LSK_EARG;
+    }
+    const long long total = ((num + PANEL - 1) / PANEL) * (long long)kg_total * (PANEL * 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex) embed_kernel<true><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
+    else embed_kernel<false><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int lsk_version(void) { return LSK_VERSION; }
+
+extern "C" long long lsk_embed_buffer_doubles(long long num, int kg_total) {
+    return ((num + lsk::PANEL - 1) / lsk::PANEL) * (long long)kg_total * (lsk::PANEL * 4);
+}

@@ -1,0 +1,362 @@
+// Fused pairwise covariance kernel:  out[i,j] = scale * P( invariants of x_i y_j^{-1} ).
+//
+// Replaces, for all N*M pairs at once, the reference chain
+//   cartesian_prod (utils.py:40-52) -> bmm (space.py:62-78) -> torus_representative (so.py:136-168, su.py:91-92)
+//   -> per-monomial character loop (so.py:288-293, su.py:175-179) -> weighted sum (spectral_kernel.py:45-54).
+//
+// Formulation: the conjugation invariants of g = x_i y_j^{-1} that the characters depend on
+// (tr g, e_2(g), ...) are *bilinear* in per-point embeddings (vec x, Lambda^2 x, ...: Cauchy-Binet), so the
+// pair stage is a small-K fp64 GEMM  u_f = A_f B_f^T  run on the fp64 tensor-core path (DMMA m8n8k4) with operands
+// staged through shared memory by 1-D bulk async copies (TMA engine) in a 4-stage mbarrier ring fed by a
+// dedicated producer warp.  The class polynomial is then evaluated in registers on the accumulator fragments
+// (coefficients come from the kernel-parameter constant bank through uniform loads) and the covariance tile is
+// written with 16-byte streaming stores.  Nothing of size N*M exists except the output.
+//
+// Operand layout ("panel-major", produced by lsk_embed.cu): rows are grouped in panels of 64; inside a panel
+// the data is [k-group g][row r][4 doubles], so (a) one pipeline stage of a panel is one contiguous 16 KB
+// block (one bulk copy) and (b) a DMMA A/B fragment (8 rows x 4 k) is one contiguous, conflict-free 256 B read.
+#include "lsk_common.cuh"
+#include "lsk_pairwise.cuh"
+
+namespace lsk {
+
+constexpr int STAGE_DOUBLES = KG_PER_STAGE * PANEL * 4;          // per operand: 2048 doubles = 16 KB
+constexpr int SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 64;
+
+// ------------------------------------------------------------------------------------------------------------
+// epilogues: R entries per call so that every uniform coefficient load feeds R DFMAs
+// ------------------------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void epi_cheb1(const LskEpilogue& p, const double (&v0)[R], double (&out)[R]) {
+    // Clenshaw for sum_k c_k T_k(x):  b_k = c_k + 2x b_{k+1} - b_{k+2};  result = c_0 + x b_1 - b_2
+    double b1[R], b2[R], x2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { b1[r] = 0.0; b2[r] = 0.0; x2[r] = 2.0 * v0[r]; }
+    for (int k = p.nterms - 1; k >= 1; --k) {
+        const double c = p.coef[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double t = fma(x2[r], b1[r], c - b2[r]);
+            b2[r] = b1[r];
+            b1[r] = t;
+        }
+    }
+    const double c0 = p.coef[0];
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = fma(v0[r], b1[r], c0 - b2[r]);
+}
+
+template <int R>
+__device__ __forceinline__ void epi_stair2(const LskEpilogue& p, const double (&s1)[R], const double (&s2)[R], double (&out)[R]) {
+    // sum_b s2^b ( sum_a C[b][a] s1^a ), coefficients stored in evaluation order (highest b first, highest a first)
+    double outer[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) outer[r] = 0.0;
+    int pos = 0;
+    for (int b = p.nterms - 1; b >= 0; --b) {
+        const int len = p.row_len[b];
+        double inner[R];
+        const double c0 = p.coef[pos];
+#pragma unroll
+        for (int r = 0; r < R; ++r) inner[r] = c0;
+#pragma unroll 4
+        for (int a = 1; a < len; ++a) {
+            const double c = p.coef[pos + a];
+#pragma unroll
+            for (int r = 0; r < R; ++r) inner[r] = fma(inner[r], s1[r], c);
+        }
+        pos += len;
+#pragma unroll
+        for (int r = 0; r < R; ++r) outer[r] = fma(outer[r], s2[r], inner[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = outer[r];
+}
+
+template <int R, int D>
+__device__ __forceinline__ void epi_orbit2(const LskEpilogue& p, const double (&s1)[R], const double (&s2)[R], double (&out)[R]) {
+    // c1, c2 = roots of z^2 - s1 z + s2;  sum_{a,b<D} W[a][b] T_a(c1) T_b(c2), W dense row-major D x D
+    double tb[R][D], ta0[R], ta1[R], c1x2[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double disc = fmax(fma(s1[r], s1[r], -4.0 * s2[r]), 0.0);
+        const double rt = sqrt(disc);
+        const double c1 = 0.5 * (s1[r] + rt), c2 = 0.5 * (s1[r] - rt);
+        tb[r][0] = 1.0;
+        tb[r][1] = c2;
+#pragma unroll
+        for (int b = 2; b < D; ++b) tb[r][b] = fma(2.0 * c2, tb[r][b - 1], -tb[r][b - 2]);
+        ta0[r] = 1.0; ta1[r] = c1; c1x2[r] = 2.0 * c1; acc[r] = 0.0;
+    }
+    for (int a = 0; a < p.nterms; ++a) {
+        double row[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) row[r] = 0.0;
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+            const double w = p.coef[a * D + b];
+#pragma unroll
+            for (int r = 0; r < R; ++r) row[r] = fma(w, tb[r][b], row[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            acc[r] = fma(ta0[r], row[r], acc[r]);
+            const double nxt = fma(c1x2[r], ta1[r], -ta0[r]);   // T_{a+2}
+            ta0[r] = ta1[r];
+            ta1[r] = nxt;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = acc[r];
+}
+
+template <int R, int NV>
+__device__ __forceinline__ void epi_sparse(const LskEpilogue& p, const double (&v)[NV][R], double (&out)[R]) {
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    for (int t = 0; t < p.nterms; ++t) {
+        const double c = p.coef[2 * t];
+        const unsigned long long e = (unsigned long long)__double_as_longlong(p.coef[2 * t + 1]);
+        double m[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) m[r] = c;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int ei = (int)((e >> (8 * i)) & 0xffu);
+            for (int k = 0; k < ei; ++k) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) m[r] *= v[i][r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] += m[r];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = acc[r];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// main kernel
+//   EPI: epilogue kind;  NF: number of bilinear forms;  NV: number of variables (SPARSE only);  D: ORBIT2 size
+// ------------------------------------------------------------------------------------------------------------
+template <int EPI, int NF, int NV, int D>
+__global__ void __launch_bounds__(THREADS, 1)
+pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
+                int n_rows, int n_cols, int kg_total,               // kg_total: k-groups per row of A and B
+                double* __restrict__ out, long long ld_out,
+                const __grid_constant__ LskEpilogue p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + STAGES * STAGE_DOUBLES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * STAGE_DOUBLES);
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row_panels = (n_rows + PANEL - 1) / PANEL, col_panels = (n_cols + PANEL - 1) / PANEL;
+    const long long n_tiles = (long long)row_panels * col_panels;
+    const int chunks = (kg_total + KG_PER_STAGE - 1) / KG_PER_STAGE;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        // ===================== producer warp: one elected lane drives the bulk-copy ring =====================
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int pr = (int)(t / col_panels), pc = (int)(t % col_panels);
+                const double* srcA = A + (size_t)pr * kg_total * (PANEL * 4);
+                const double* srcB = B + (size_t)pc * kg_total * (PANEL * 4);
+                for (int c = 0; c < chunks; ++c, ++q) {
+                    const int s = q % STAGES;
+                    const uint32_t round = q / STAGES;
+                    if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                    const int kg = min(KG_PER_STAGE, kg_total - c * KG_PER_STAGE);
+                    const uint32_t bytes = (uint32_t)kg * PANEL * 4 * 8;
+                    mbar_expect_tx(&full_bar[s], 2 * bytes);
+                    bulk_g2s(sA + s * STAGE_DOUBLES, srcA + (size_t)c * STAGE_DOUBLES, bytes, &full_bar[s]);
+                    bulk_g2s(sB + s * STAGE_DOUBLES, srcB + (size_t)c * STAGE_DOUBLES, bytes, &full_bar[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps: 2 (rows) x 4 (cols), warp tile 32 x 16 =====================
+    const int wr = warp >> 2, wc = warp & 3;
+    const int frag = (lane >> 2) * 4 + (lane & 3);           // offset of this lane inside an 8x4 fragment
+    const int a_off = (wr * 32) * 4 + frag;
+    const int b_off = (wc * 16) * 4 + frag;
+    const bool vec_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+
+    uint32_t q = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int pr = (int)(t / col_panels), pc = (int)(t % col_panels);
+        double acc[NF][4][2][2];
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int n = 0; n < 2; ++n) { acc[f][m][n][0] = 0.0; acc[f][m][n][1] = 0.0; }
+
+        // ---- bilinear forms on the tensor-core path ----
+        const uint32_t q_tile = q;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            for (int g = p.group_begin[f]; g < p.group_end[f]; ++g) {
+                const int c = g / KG_PER_STAGE, gi = g % KG_PER_STAGE;
+                const uint32_t qq = q_tile + c;
+                const int s = qq % STAGES;
+                if (gi == 0 || g == p.group_begin[f]) mbar_wait(&full_bar[s], (qq / STAGES) & 1);
+                const double* pa = sA + s * STAGE_DOUBLES + gi * (PANEL * 4) + a_off;
+                const double* pb = sB + s * STAGE_DOUBLES + gi * (PANEL * 4) + b_off;
+                double a[4], b[2];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) a[m] = pa[m * 32];
+#pragma unroll
+                for (int n = 0; n < 2; ++n) b[n] = pb[n * 32];
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int n = 0; n < 2; ++n) dmma884(acc[f][m][n], a[m], b[n]);
+                // last group of a stage (or of the whole k range): hand the stage back to the producer
+                if (gi == KG_PER_STAGE - 1 || g == kg_total - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                }
+            }
+        }
+        q = q_tile + chunks;
+
+        // ---- class polynomial on the accumulator fragments, 8 entries at a time ----
+        const int row0 = pr * PANEL + wr * 32 + (lane >> 2);
+        const int col0 = pc * PANEL + wc * 16 + 2 * (lane & 3);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            constexpr int R = 8;
+            double var[NV][R], res[R];
+#pragma unroll
+            for (int e = 0; e < R; ++e) {
+                const int m = 2 * h + (e >> 2), n = (e >> 1) & 1, i = e & 1;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    double x = p.aff[v][0];
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) x = fma(p.aff[v][1 + f], acc[f][m][n][i], x);
+                    var[v][e] = x;
+                }
+            }
+            if constexpr (EPI == LSK_EPI_CHEB1) epi_cheb1<R>(p, var[0], res);
+            else if constexpr (EPI == LSK_EPI_STAIR2) epi_stair2<R>(p, var[0], var[1], res);
+            else if constexpr (EPI == LSK_EPI_SPARSE) epi_sparse<R, NV>(p, var, res);
+            else {
+                // ORBIT2 keeps a Chebyshev table per entry: run it 2 entries at a time to bound registers
+#pragma unroll
+                for (int e2 = 0; e2 < R; e2 += 2) {
+                    double a1[2] = {var[0][e2], var[0][e2 + 1]}, a2[2] = {var[1][e2], var[1][e2 + 1]}, o[2];
+                    epi_orbit2<2, D>(p, a1, a2, o);
+                    res[e2] = o[0]; res[e2 + 1] = o[1];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < R; e += 2) {
+                const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
+                const int row = row0 + m * 8, col = col0 + n * 8;
+                if (row < n_rows) {
+                    double* dst = out + (size_t)row * ld_out + col;
+                    const double r0 = p.scale * res[e], r1 = p.scale * res[e + 1];
+                    if (vec_ok && col + 1 < n_cols) st_cs_f64x2(dst, r0, r1);
+                    else {
+                        if (col < n_cols) st_cs_f64(dst, r0);
+                        if (col + 1 < n_cols) st_cs_f64(dst + 1, r1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int EPI, int NF, int NV, int D>
+static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
+                  const LskEpilogue& p, int max_ctas, cudaStream_t stream) {
+    auto kern = pairwise_kernel<EPI, NF, NV, D>;
+    static bool configured = false;   // idempotent attribute set; racing threads set the same value
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const long long tiles = (long long)((n_rows + PANEL - 1) / PANEL) * ((n_cols + PANEL - 1) / PANEL);
+    int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(A, B, n_rows, n_cols, kg_total, out, ld_out, p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace lsk
+
+extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows, long long n_cols, int kg_total,
+                                 const LskEpilogue* epi, void* out, long long ld_out, void* stream) {
+    using namespace lsk;
+    if (!A || !B || !out || !epi) return LSK_EARG;
+    if (n_rows < 0 || n_cols < 0 || kg_total <= 0 || ld_out < n_cols) return LSK_ESIZE;
+    if (n_rows == 0 || n_cols == 0) return 0;
+    if (n_rows > 0x7fffffffLL || n_cols > 0x7fffffffLL) return LSK_ESIZE;
+    const LskEpilogue& p = *epi;
+    if (p.nforms < 1 || p.nforms > LSK_MAX_FORMS || p.nvars < 1 || p.nvars > LSK_MAX_VARS) return LSK_EARG;
+    for (int f = 0; f < p.nforms; ++f)
+        if (p.group_begin[f] < 0 || p.group_end[f] > kg_total || p.group_begin[f] >= p.group_end[f]) return LSK_EARG;
+    for (int f = 1; f < p.nforms; ++f)
+        if (p.group_begin[f] != p.group_end[f - 1]) return LSK_EARG;   // forms tile the k range in order
+    if (p.group_begin[0] != 0 || p.group_end[p.nforms - 1] != kg_total) return LSK_EARG;
+
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double* a = static_cast<const double*>(A);
+    const double* b = static_cast<const double*>(B);
+    double* o = static_cast<double*>(out);
+    const int nr = (int)n_rows, nc = (int)n_cols;
+
+#define LSK_GO(EPI, NF, NV, D) return launch<EPI, NF, NV, D>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st)
+    switch (p.kind) {
+    case LSK_EPI_CHEB1:
+        if (p.nterms < 1 || p.nterms > LSK_MAX_COEF || p.nvars != 1) return LSK_EARG;
+        if (p.nforms == 1) LSK_GO(LSK_EPI_CHEB1, 1, 1, 1);
+        return LSK_EUNSUPPORTED;
+    case LSK_EPI_STAIR2: {
+        if (p.nterms < 1 || p.nterms > LSK_MAX_ROWS || p.nvars != 2) return LSK_EARG;
+        int tot = 0;
+        for (int b2 = 0; b2 < p.nterms; ++b2) { if (p.row_len[b2] < 1) return LSK_EARG; tot += p.row_len[b2]; }
+        if (tot > LSK_MAX_COEF) return LSK_ESIZE;
+        if (p.nforms == 2) LSK_GO(LSK_EPI_STAIR2, 2, 2, 1);
+        return LSK_EUNSUPPORTED;
+    }
+    case LSK_EPI_ORBIT2:
+        if (p.nvars != 2 || p.nforms != 2 || p.nterms < 1) return LSK_EARG;
+        if (p.nterms <= 8) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 8);
+        if (p.nterms <= 12) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 12);
+        if (p.nterms <= 16) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 16);
+        if (p.nterms <= 20) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 20);
+        return LSK_ESIZE;
+    case LSK_EPI_SPARSE:
+        if (p.nterms < 1 || 2 * p.nterms > LSK_MAX_COEF) return LSK_ESIZE;
+        if (p.nforms == 1 && p.nvars == 1) LSK_GO(LSK_EPI_SPARSE, 1, 1, 1);
+        if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_SPARSE, 2, 2, 1);
+        if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_SPARSE, 3, 3, 1);
+        if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_SPARSE, 4, 4, 1);
+        return LSK_EUNSUPPORTED;
+    default:
+        return LSK_EARG;
+    }
+#undef LSK_GO
+}

@@ -1,0 +1,70 @@
+"""Kernel front-ends — drop-in for the reference's `spectral_kernel.py` (same classes, constructor arguments,
+`kernel(x, y=None, normalize=True)`, `.normalizer`, training-mode side effects and RNG consumption order).
+
+The forward passes do not materialise anything of size N*M except the result: see csrc/lsk_pairwise.cu."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .space import AbstractManifold, CompactLieGroup
+from .spectral_measure import AbstractSpectralMeasure
+
+dtype = torch.float64
+
+
+class AbstractSpectralKernel(torch.nn.Module):
+    def __init__(self, measure: AbstractSpectralMeasure, manifold: AbstractManifold):
+        super().__init__()
+        self.measure = measure
+        self.manifold = manifold
+
+    def forward(self, *args):
+        raise NotImplementedError
+
+
+def spectral_weights(measure, manifold):
+    """Host copy of a(lambda_l) for the manifold's irreps (spectral_measure.py:24-26, 35-36): one tiny device op and
+    one L-element device->host read per call; all N*M work is in the CUDA kernel."""
+    with torch.no_grad():
+        a = measure(manifold._lambdas)
+    return a.detach().cpu().numpy()
+
+
+class EigenbasisSumKernel(AbstractSpectralKernel):
+    """k(x, y) = |sigma^2| / norm * sum_l a(lambda_l) d_l Re chi_l(x y^{-1})   (spectral_kernel.py:26-54)."""
+
+    def __init__(self, measure, manifold, form="auto"):
+        super().__init__(measure, manifold)
+        self.form = form
+        point = manifold.rand()
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def compute_normalizer(self):
+        point = self.manifold.rand()
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def forward(self, x, y=None, normalize=True, out=None):
+        if y is None:
+            y = x
+        if self.training:
+            if normalize:
+                self.compute_normalizer()
+        manifold = self.manifold
+        if not isinstance(manifold, CompactLieGroup):
+            return manifold._eigensum(self, x, y, normalize, out)
+        plan = manifold.plan
+        w = spectral_weights(self.measure, manifold) * manifold._dims
+        if normalize:
+            scale = float(torch.abs(self.measure.variance[0]).item() / float(self.normalizer))
+        else:
+            scale = 1.0
+        ep = plan.epilogue(w, scale, form=self.form)
+        ea = ops.embed(plan, x, "a")
+        eb = ea if (y is x and not plan.is_complex) else ops.embed(plan, y, "b")
+        return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out)
+
+
+# north_star spelling
+EigenSumKernel = EigenbasisSumKernel

@@ -1,0 +1,96 @@
+"""numpy emulation of the CUDA data path (embedding -> bilinear forms -> epilogue) driven by the very same
+`LskEpilogue` parameter block the kernels receive.  Test infrastructure: lets the CPU suite validate the host
+tables (classfn.py) end to end against the reference goldens without a GPU."""
+import itertools
+
+import numpy as np
+
+from liestationarykernels_b200 import _lib
+
+
+def compound(x, k):
+    """Lambda^k of each matrix in the batch: [num, C(n,k), C(n,k)] (same lexicographic order as lsk_embed.cu)."""
+    n = x.shape[-1]
+    idx = list(itertools.combinations(range(n), k))
+    out = np.zeros((x.shape[0], len(idx), len(idx)), dtype=x.dtype)
+    for a, I in enumerate(idx):
+        for b, J in enumerate(idx):
+            out[:, a, b] = np.linalg.det(x[:, I, :][:, :, J]) if k > 1 else x[:, I[0], J[0]]
+    return out
+
+
+def embed(plan, x, side):
+    segs = plan.segments_a if side == "a" else plan.segments_b
+    cols = []
+    for (k, part) in segs:
+        c = compound(x, k).reshape(x.shape[0], -1)
+        if part == 0:
+            v = c.real
+        else:
+            if part == 3:
+                v = np.stack((-c.imag, c.real), axis=-1).reshape(x.shape[0], -1)
+            else:
+                v = np.stack((c.real, c.imag), axis=-1).reshape(x.shape[0], -1)
+        pad = (-v.shape[1]) % 4
+        cols.append(np.pad(v, ((0, 0), (0, pad))))
+    return np.concatenate(cols, axis=1)
+
+
+def run_epilogue(ep, forms):
+    """forms: [nforms, N, M] -> [N, M]"""
+    var = [ep.aff[v][0] + sum(ep.aff[v][1 + f] * forms[f] for f in range(ep.nforms)) for v in range(ep.nvars)]
+    coef = np.array(ep.coef[:])
+    if ep.kind == _lib.EPI_CHEB1:
+        x = var[0]
+        b1 = np.zeros_like(x)
+        b2 = np.zeros_like(x)
+        for k in range(ep.nterms - 1, 0, -1):
+            b1, b2 = 2 * x * b1 + (coef[k] - b2), b1
+        res = x * b1 + (coef[0] - b2)
+    elif ep.kind == _lib.EPI_STAIR2:
+        s1, s2 = var
+        res = np.zeros_like(s1)
+        pos = 0
+        for b in range(ep.nterms - 1, -1, -1):
+            ln = ep.row_len[b]
+            inner = np.full_like(s1, coef[pos])
+            for a in range(1, ln):
+                inner = inner * s1 + coef[pos + a]
+            pos += ln
+            res = res * s2 + inner
+    elif ep.kind == _lib.EPI_ORBIT2:
+        s1, s2 = var
+        D = ep.nterms
+        Dp = 8 if D <= 8 else 12 if D <= 12 else 16 if D <= 16 else 20
+        rt = np.sqrt(np.maximum(s1 * s1 - 4 * s2, 0))
+        c1, c2 = 0.5 * (s1 + rt), 0.5 * (s1 - rt)
+        T1 = [np.ones_like(c1), c1]
+        T2 = [np.ones_like(c2), c2]
+        for k in range(2, Dp):
+            T1.append(2 * c1 * T1[-1] - T1[-2])
+            T2.append(2 * c2 * T2[-1] - T2[-2])
+        res = np.zeros_like(s1)
+        for a in range(D):
+            row = sum(coef[a * Dp + b] * T2[b] for b in range(Dp))
+            res = res + T1[a] * row
+    elif ep.kind == _lib.EPI_SPARSE:
+        res = np.zeros_like(var[0])
+        for t in range(ep.nterms):
+            packed = int(np.array([coef[2 * t + 1]]).view(np.uint64)[0])
+            m = np.full_like(var[0], coef[2 * t])
+            for i in range(ep.nvars):
+                e = (packed >> (8 * i)) & 0xFF
+                m = m * var[i] ** e
+            res = res + m
+    else:
+        raise ValueError(ep.kind)
+    return ep.scale * res
+
+
+def pairwise(plan, x, y, ep):
+    A, B = embed(plan, x, "a"), embed(plan, y, "b")
+    forms = []
+    for f in range(ep.nforms):
+        lo, hi = 4 * ep.group_begin[f], 4 * ep.group_end[f]
+        forms.append(A[:, lo:hi] @ B[:, lo:hi].T)
+    return run_epilogue(ep, np.array(forms))
