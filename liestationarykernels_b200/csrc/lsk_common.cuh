@@ -12,13 +12,14 @@
 
 namespace lsk {
 
-constexpr int BM = 64;          // rows of x (or of phases) per CTA tile == embedding panel height
-constexpr int BN = 64;          // columns per CTA tile
-constexpr int PANEL = 64;       // rows per panel of the embedded operand layout (must equal BM and BN)
-constexpr int KG_PER_STAGE = 8; // k-groups (of 4 doubles) per pipeline stage -> 16 KB per operand per stage
-constexpr int STAGES = 4;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;   // + one producer warp
+constexpr int PANEL = 64;       // rows per panel of the embedded operand layout
+constexpr int BM = 128;         // rows per CTA tile  (two A panels)
+constexpr int BN = 64;          // columns per CTA tile (one B panel)
+constexpr int ROW_PAD = 128;    // embedded operands are zero-padded to a multiple of this many rows
+constexpr int KG_PER_STAGE = 8; // k-groups (of 4 doubles) per pipeline stage -> 16 KB per panel per stage
+constexpr int STAGES = 3;       // 3 x (2 A panels + 1 B panel) x 16 KB = 144 KB
+constexpr int CONSUMER_WARPS = 16;
+constexpr int THREADS = CONSUMER_WARPS * 32;         // the TMA producer is lane 0 of warp 0
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -43,6 +44,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra LSK_WAIT_%=;\n"
         "LSK_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

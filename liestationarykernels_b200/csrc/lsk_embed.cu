@@ -77,7 +77,7 @@ __device__ void minor(const double* x, int n, int k, const int (&I)[3], const in
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
 embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, EmbedSpec spec, double* __restrict__ out) {
-    const long long total = ((num + PANEL - 1) / PANEL) * (long long)kg_total * (PANEL * 4);
+    const long long total = ((num + ROW_PAD - 1) / ROW_PAD) * (ROW_PAD / PANEL) * (long long)kg_total * (PANEL * 4);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx & 3);
         const int r = (int)((idx >> 2) & (PANEL - 1));
@@ -130,7 +130,7 @@ extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_comp
         if (group_begin[s] < 0 || end > kg_total) return LSK_ESIZE;
         if (s > 0 && group_begin[s] < spec.group_begin[s - 1] + (spec.length[s - 1] + 3) / 4) return LSK_EARG;
     }
-    const long long total = ((num + PANEL - 1) / PANEL) * (long long)kg_total * (PANEL * 4);
+    const long long total = ((num + ROW_PAD - 1) / ROW_PAD) * (ROW_PAD / PANEL) * (long long)kg_total * (PANEL * 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -142,5 +142,5 @@ extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_comp
 extern "C" int lsk_version(void) { return LSK_VERSION; }
 
 extern "C" long long lsk_embed_buffer_doubles(long long num, int kg_total) {
-    return ((num + lsk::PANEL - 1) / lsk::PANEL) * (long long)kg_total * (lsk::PANEL * 4);
+    return ((num + lsk::ROW_PAD - 1) / lsk::ROW_PAD) * (lsk::ROW_PAD / lsk::PANEL) * (long long)kg_total * (lsk::PANEL * 4);
 }

@@ -7,12 +7,12 @@
 // Formulation: the conjugation invariants of g = x_i y_j^{-1} that the characters depend on
 // (tr g, e_2(g), ...) are *bilinear* in per-point embeddings (vec x, Lambda^2 x, ...: Cauchy-Binet), so the
 // pair stage is a small-K fp64 GEMM  u_f = A_f B_f^T  run on the fp64 tensor-core path (DMMA m8n8k4) with operands
-// staged through shared memory by 1-D bulk async copies (TMA engine) in a 4-stage mbarrier ring fed by a
+// staged through shared memory by 1-D bulk async copies (TMA engine) in a 3-stage mbarrier ring fed by a
 // dedicated producer warp.  The class polynomial is then evaluated in registers on the accumulator fragments
 // (coefficients come from the kernel-parameter constant bank through uniform loads) and the covariance tile is
 // written with 16-byte streaming stores.  Nothing of size N*M exists except the output.
 //
-// Operand layout ("panel-major", produced by lsk_embed.cu): rows are grouped in panels of 64; inside a panel
+// Operand layout ("panel-major", produced by lsk_embed.cu): rows are grouped in panels of 64 (zero-padded to a multiple of 128 rows); inside a panel
 // the data is [k-group g][row r][4 doubles], so (a) one pipeline stage of a panel is one contiguous 16 KB
 // block (one bulk copy) and (b) a DMMA A/B fragment (8 rows x 4 k) is one contiguous, conflict-free 256 B read.
 #include "lsk_common.cuh"
@@ -20,8 +20,10 @@
 
 namespace lsk {
 
-constexpr int STAGE_DOUBLES = KG_PER_STAGE * PANEL * 4;          // per operand: 2048 doubles = 16 KB
-constexpr int SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 64;
+constexpr int PANEL_STAGE = KG_PER_STAGE * PANEL * 4;            // one panel, one stage: 2048 doubles = 16 KB
+constexpr int A_STAGE = (BM / PANEL) * PANEL_STAGE;              // two A panels
+constexpr int B_STAGE = PANEL_STAGE;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * 8 + 2 * STAGES * 8 + 64;
 
 // ------------------------------------------------------------------------------------------------------------
 // epilogues: R entries per call so that every uniform coefficient load feeds R DFMAs
@@ -149,14 +151,13 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
-    double* sB = sA + STAGES * STAGE_DOUBLES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * STAGE_DOUBLES);
+    double* sB = sA + STAGES * A_STAGE;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
     uint64_t* empty_bar = full_bar + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row_panels = (n_rows + PANEL - 1) / PANEL, col_panels = (n_cols + PANEL - 1) / PANEL;
-    const long long n_tiles = (long long)row_panels * col_panels;
-    const int chunks = (kg_total + KG_PER_STAGE - 1) / KG_PER_STAGE;
+    const int row_tiles = (n_rows + BM - 1) / BM, col_panels = (n_cols + BN - 1) / BN;
+    const long long n_tiles = (long long)row_tiles * col_panels;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -165,37 +166,52 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     }
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
-        // ===================== producer warp: one elected lane drives the bulk-copy ring =====================
-        if (lane == 0) {
-            uint32_t q = 0;
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int pr = (int)(t / col_panels), pc = (int)(t % col_panels);
-                const double* srcA = A + (size_t)pr * kg_total * (PANEL * 4);
-                const double* srcB = B + (size_t)pc * kg_total * (PANEL * 4);
-                for (int c = 0; c < chunks; ++c, ++q) {
-                    const int s = q % STAGES;
-                    const uint32_t round = q / STAGES;
-                    if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-                    const int kg = min(KG_PER_STAGE, kg_total - c * KG_PER_STAGE);
-                    const uint32_t bytes = (uint32_t)kg * PANEL * 4 * 8;
-                    mbar_expect_tx(&full_bar[s], 2 * bytes);
-                    bulk_g2s(sA + s * STAGE_DOUBLES, srcA + (size_t)c * STAGE_DOUBLES, bytes, &full_bar[s]);
-                    bulk_g2s(sB + s * STAGE_DOUBLES, srcB + (size_t)c * STAGE_DOUBLES, bytes, &full_bar[s]);
-                }
-            }
+    // ===================== producer duty (lane 0 of warp 0), folded into a consumer warp =====================
+    // 16 consumer warps = 4 per SM sub-partition keeps the register budget at 128/thread; a 17th warp would cut it to 96.
+    // The producer state runs ahead of the consumer state by at most STAGES chunks.
+    long long p_tile = blockIdx.x;
+    int p_form = 0, p_group = p.group_begin[0], p_stage = 0;
+    uint32_t p_phase = 0;
+    int issued_ahead = 0;                       // chunks issued but not yet consumed by warp 0
+    auto produce = [&](bool blocking) -> bool {
+        if (p_tile >= n_tiles) return false;
+        if (blocking) mbar_wait(&empty_bar[p_stage], p_phase ^ 1);      // first pass over the ring returns immediately
+        else if (!mbar_test(&empty_bar[p_stage], p_phase ^ 1)) return false;
+        const int pr = (int)(p_tile / col_panels), pc = (int)(p_tile % col_panels);
+        const double* srcA0 = A + ((size_t)(2 * pr) * kg_total + p_group) * (PANEL * 4);   // operands are padded to
+        const double* srcA1 = srcA0 + (size_t)kg_total * (PANEL * 4);                       // ROW_PAD rows: both exist
+        const double* srcB = B + ((size_t)pc * kg_total + p_group) * (PANEL * 4);
+        const int ng = min(KG_PER_STAGE, p.group_end[p_form] - p_group);
+        const uint32_t bytes = (uint32_t)ng * PANEL * 4 * 8;
+        mbar_expect_tx(&full_bar[p_stage], 3 * bytes);
+        bulk_g2s(sA + p_stage * A_STAGE, srcA0, bytes, &full_bar[p_stage]);
+        bulk_g2s(sA + p_stage * A_STAGE + PANEL_STAGE, srcA1, bytes, &full_bar[p_stage]);
+        bulk_g2s(sB + p_stage * B_STAGE, srcB, bytes, &full_bar[p_stage]);
+        p_group += KG_PER_STAGE;
+        if (p_group >= p.group_end[p_form]) {
+            if (++p_form == NF) { p_form = 0; p_tile += gridDim.x; }
+            p_group = p.group_begin[p_form];
         }
-        return;
-    }
+        if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
+        ++issued_ahead;
+        return true;
+    };
+    // keep the ring full without ever blocking (called by warp 0 wherever it is cheap)
+    auto produce_ahead = [&]() {
+        if (threadIdx.x == 0) {
+            while (issued_ahead < STAGES) if (!produce(false)) break;
+        }
+    };
 
-    // ===================== consumer warps: 2 (rows) x 4 (cols), warp tile 32 x 16 =====================
+    // ===================== consumer warps: 4 (rows) x 4 (cols), warp tile 32 x 16 =====================
     const int wr = warp >> 2, wc = warp & 3;
     const int frag = (lane >> 2) * 4 + (lane & 3);           // offset of this lane inside an 8x4 fragment
-    const int a_off = (wr * 32) * 4 + frag;
+    const int a_off = (wr >> 1) * PANEL_STAGE + ((wr & 1) * 32) * 4 + frag;
     const int b_off = (wc * 16) * 4 + frag;
     const bool vec_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
-    uint32_t q = 0;
+    int stage = 0;
+    uint32_t phase = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int pr = (int)(t / col_panels), pc = (int)(t % col_panels);
         double acc[NF][4][2][2];
@@ -206,41 +222,64 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 #pragma unroll
                 for (int n = 0; n < 2; ++n) { acc[f][m][n][0] = 0.0; acc[f][m][n][1] = 0.0; }
 
-        // ---- bilinear forms on the tensor-core path ----
-        const uint32_t q_tile = q;
+        // ---- bilinear forms on the tensor-core path: every form is cut into chunks of <= KG_PER_STAGE k-groups,
+        //      one pipeline stage each; inside a stage all offsets are immediates ----
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-            for (int g = p.group_begin[f]; g < p.group_end[f]; ++g) {
-                const int c = g / KG_PER_STAGE, gi = g % KG_PER_STAGE;
-                const uint32_t qq = q_tile + c;
-                const int s = qq % STAGES;
-                if (gi == 0 || g == p.group_begin[f]) mbar_wait(&full_bar[s], (qq / STAGES) & 1);
-                const double* pa = sA + s * STAGE_DOUBLES + gi * (PANEL * 4) + a_off;
-                const double* pb = sB + s * STAGE_DOUBLES + gi * (PANEL * 4) + b_off;
-                double a[4], b[2];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) a[m] = pa[m * 32];
-#pragma unroll
-                for (int n = 0; n < 2; ++n) b[n] = pb[n * 32];
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-#pragma unroll
-                    for (int n = 0; n < 2; ++n) dmma884(acc[f][m][n], a[m], b[n]);
-                // last group of a stage (or of the whole k range): hand the stage back to the producer
-                if (gi == KG_PER_STAGE - 1 || g == kg_total - 1) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+            const int g_end = p.group_end[f];
+            for (int g = p.group_begin[f]; g < g_end; g += KG_PER_STAGE) {
+                const int ng = min(KG_PER_STAGE, g_end - g);
+                if (threadIdx.x == 0) {
+                    if (issued_ahead == 0) produce(true);      // the chunk we are about to wait for must be in flight
+                    while (issued_ahead < STAGES) if (!produce(false)) break;
                 }
+                __syncwarp();
+                mbar_wait(&full_bar[stage], phase);
+                const double* pa = sA + stage * A_STAGE + a_off;
+                const double* pb = sB + stage * B_STAGE + b_off;
+                if (ng == KG_PER_STAGE) {
+#pragma unroll
+                    for (int gi = 0; gi < KG_PER_STAGE; ++gi) {
+                        double a[4], b[2];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) a[m] = pa[gi * (PANEL * 4) + m * 32];
+#pragma unroll
+                        for (int n = 0; n < 2; ++n) b[n] = pb[gi * (PANEL * 4) + n * 32];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+#pragma unroll
+                            for (int n = 0; n < 2; ++n) dmma884(acc[f][m][n], a[m], b[n]);
+                    }
+                } else {
+#pragma unroll
+                    for (int gi = 0; gi < KG_PER_STAGE - 1; ++gi) {
+                        if (gi < ng) {
+                            double a[4], b[2];
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) a[m] = pa[gi * (PANEL * 4) + m * 32];
+#pragma unroll
+                            for (int n = 0; n < 2; ++n) b[n] = pb[gi * (PANEL * 4) + n * 32];
+#pragma unroll
+                            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                                for (int n = 0; n < 2; ++n) dmma884(acc[f][m][n], a[m], b[n]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);      // hand the stage back to the producer
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                --issued_ahead;
             }
         }
-        q = q_tile + chunks;
 
         // ---- class polynomial on the accumulator fragments, 8 entries at a time ----
-        const int row0 = pr * PANEL + wr * 32 + (lane >> 2);
-        const int col0 = pc * PANEL + wc * 16 + 2 * (lane & 3);
+        const int row0 = pr * BM + wr * 32 + (lane >> 2);
+        const int col0 = pc * BN + wc * 16 + 2 * (lane & 3);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             constexpr int R = 8;
+            produce_ahead();
             double var[NV][R], res[R];
 #pragma unroll
             for (int e = 0; e < R; ++e) {
@@ -287,14 +326,14 @@ template <int EPI, int NF, int NV, int D>
 static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                   const LskEpilogue& p, int max_ctas, cudaStream_t stream) {
     auto kern = pairwise_kernel<EPI, NF, NV, D>;
-    static bool configured = false;   // idempotent attribute set; racing threads set the same value
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
-    const long long tiles = (long long)((n_rows + PANEL - 1) / PANEL) * ((n_cols + PANEL - 1) / PANEL);
-    int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const long long tiles = (long long)((n_rows + BM - 1) / BM) * ((n_cols + BN - 1) / BN);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, SMEM_BYTES);
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)max_ctas * per_sm;
+    int grid = (int)(tiles < cap ? tiles : cap);
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(A, B, n_rows, n_cols, kg_total, out, ld_out, p);
     return (int)cudaGetLastError();
 }

@@ -38,6 +38,7 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
     def __init__(self, measure, manifold, form="auto"):
         super().__init__(measure, manifold)
         self.form = form
+        self._ep_cache = {}
         point = manifold.rand()
         self.normalizer = self.forward(point, point, normalize=False)[0, 0]
 
@@ -55,15 +56,27 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         if not isinstance(manifold, CompactLieGroup):
             return manifold._eigensum(self, x, y, normalize, out)
         plan = manifold.plan
-        w = spectral_weights(self.measure, manifold) * manifold._dims
-        if normalize:
-            scale = float(torch.abs(self.measure.variance[0]).item() / float(self.normalizer))
-        else:
-            scale = 1.0
-        ep = plan.epilogue(w, scale, form=self.form)
+        ep = self._epilogue(normalize)
         ea = ops.embed(plan, x, "a")
         eb = ea if (y is x and not plan.is_complex) else ops.embed(plan, y, "b")
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out)
+
+
+    def _epilogue(self, normalize):
+        """Coefficient block for the current hyper-parameters.  Rebuilt (one L-element device->host read plus a few
+        hundred host flops) only when a hyper-parameter tensor or the normaliser changed since the last call."""
+        m = self.measure
+        key = [normalize, self.form]
+        for t in (m.lengthscale, m.variance, getattr(m, "nu", None), self.normalizer if normalize else None):
+            key.append(None if t is None else (id(t), t._version, t.data_ptr()) if isinstance(t, torch.Tensor) else t)
+        key = tuple(key)
+        hit = self._ep_cache.get("key") == key
+        if not hit:
+            manifold = self.manifold
+            w = spectral_weights(m, manifold) * manifold._dims
+            scale = float(torch.abs(m.variance[0]).item() / float(self.normalizer)) if normalize else 1.0
+            self._ep_cache = {"key": key, "ep": manifold.plan.epilogue(w, scale, form=self.form)}
+        return self._ep_cache["ep"]
 
 
 # north_star spelling
