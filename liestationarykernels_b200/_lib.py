@@ -18,7 +18,8 @@ MAX_VARS = 4
 MAX_COEF = 400
 MAX_ROWS = 24
 
-EPI_CHEB1, EPI_STAIR2, EPI_ORBIT2, EPI_SPARSE = 1, 2, 3, 4
+EPI_CHEB1, EPI_STAIR2, EPI_ORBIT2, EPI_SPARSE, EPI_LINEAR, EPI_FEAT_CHEB1, EPI_FEAT_SPARSE = 1, 2, 3, 4, 5, 6, 7
+OUT_ROW_MAJOR, OUT_PANEL_MAJOR = 0, 1
 
 
 class LskEpilogue(ctypes.Structure):
@@ -31,6 +32,10 @@ class LskEpilogue(ctypes.Structure):
         ("group_begin", ctypes.c_int32 * MAX_FORMS),
         ("group_end", ctypes.c_int32 * MAX_FORMS),
         ("row_len", ctypes.c_int32 * MAX_ROWS),
+        ("out_layout", ctypes.c_int32),
+        ("out_kg", ctypes.c_int32),
+        ("feat_stride", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
         ("scale", ctypes.c_double),
         ("aff", (ctypes.c_double * (1 + MAX_FORMS)) * MAX_VARS),
         ("coef", ctypes.c_double * MAX_COEF),

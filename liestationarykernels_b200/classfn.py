@@ -227,6 +227,52 @@ class GroupPlan:
             ep.coef[2 * t + 1] = np.array([packed], dtype=np.uint64).view(np.float64)[0]
         return ep
 
+    # ------------------------------------------------------------------ per-irrep feature epilogues
+    def feature_epilogues(self, row_scales, stride: int):
+        """Yields (epilogue, first output column) for batches of irreps: Phi[:, l*stride + p] = row_scales[l] chi_l."""
+        from ._lib import EPI_FEAT_CHEB1, EPI_FEAT_SPARSE
+        scales = np.asarray(row_scales, dtype=np.float64)
+        L = len(self.irreps)
+        rows = []
+        for l in range(L):
+            if self.kind == "cheb1":
+                nz = np.nonzero(self.M[l])[0]
+                deg = int(nz.max()) if len(nz) else 0
+                rows.append([float(scales[l] * self.M[l, k]) for k in range(deg + 1)])
+            else:
+                expo = self.monos if self.kind == "rank2" else self.sparse_expo
+                terms = [(float(scales[l] * self.M[l, t]), expo[t]) for t in np.nonzero(self.M[l])[0]]
+                rows.append(terms if terms else [(0.0, expo[0])])
+        cap = MAX_COEF if self.kind == "cheb1" else MAX_COEF // 2
+        start = 0
+        while start < L:
+            stop, used = start, 0
+            while stop < L and stop - start < MAX_ROWS and used + len(rows[stop]) <= cap:
+                used += len(rows[stop])
+                stop += 1
+            if stop == start:
+                raise ValueError("irrep %d has too many polynomial terms for the feature epilogue" % start)
+            ep = self._base_epilogue()
+            ep.kind = EPI_FEAT_CHEB1 if self.kind == "cheb1" else EPI_FEAT_SPARSE
+            ep.nterms = stop - start
+            ep.feat_stride = stride
+            pos = 0
+            for i, l in enumerate(range(start, stop)):
+                ep.row_len[i] = len(rows[l])
+                for item in rows[l]:
+                    if self.kind == "cheb1":
+                        ep.coef[pos] = item
+                    else:
+                        c, e = item
+                        packed = 0
+                        for j, ej in enumerate(e):
+                            packed |= int(ej) << (8 * j)
+                        ep.coef[2 * pos] = c
+                        ep.coef[2 * pos + 1] = np.array([packed], dtype=np.uint64).view(np.float64)[0]
+                    pos += 1
+            yield ep, start * stride
+            start = stop
+
     # ------------------------------------------------------------------ fast-form safety check (rank 2)
     def _probe(self):
         if getattr(self, "_probe_cache", None) is not None:

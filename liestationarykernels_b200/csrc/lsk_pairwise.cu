@@ -29,13 +29,13 @@ constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * 8 + 2 * STAGES * 8 + 6
 // epilogues: R entries per call so that every uniform coefficient load feeds R DFMAs
 // ------------------------------------------------------------------------------------------------------------
 template <int R>
-__device__ __forceinline__ void epi_cheb1(const LskEpilogue& p, const double (&v0)[R], double (&out)[R]) {
+__device__ __forceinline__ void epi_cheb1(const double* coef, int nterms, const double (&v0)[R], double (&out)[R]) {
     // Clenshaw for sum_k c_k T_k(x):  b_k = c_k + 2x b_{k+1} - b_{k+2};  result = c_0 + x b_1 - b_2
     double b1[R], b2[R], x2[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { b1[r] = 0.0; b2[r] = 0.0; x2[r] = 2.0 * v0[r]; }
-    for (int k = p.nterms - 1; k >= 1; --k) {
-        const double c = p.coef[k];
+    for (int k = nterms - 1; k >= 1; --k) {
+        const double c = coef[k];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double t = fma(x2[r], b1[r], c - b2[r]);
@@ -43,7 +43,7 @@ __device__ __forceinline__ void epi_cheb1(const LskEpilogue& p, const double (&v
             b1[r] = t;
         }
     }
-    const double c0 = p.coef[0];
+    const double c0 = coef[0];
 #pragma unroll
     for (int r = 0; r < R; ++r) out[r] = fma(v0[r], b1[r], c0 - b2[r]);
 }
@@ -113,13 +113,13 @@ __device__ __forceinline__ void epi_orbit2(const LskEpilogue& p, const double (&
 }
 
 template <int R, int NV>
-__device__ __forceinline__ void epi_sparse(const LskEpilogue& p, const double (&v)[NV][R], double (&out)[R]) {
+__device__ __forceinline__ void epi_sparse(const double* coef, int nterms, const double (&v)[NV][R], double (&out)[R]) {
     double acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
-    for (int t = 0; t < p.nterms; ++t) {
-        const double c = p.coef[2 * t];
-        const unsigned long long e = (unsigned long long)__double_as_longlong(p.coef[2 * t + 1]);
+    for (int t = 0; t < nterms; ++t) {
+        const double c = coef[2 * t];
+        const unsigned long long e = (unsigned long long)__double_as_longlong(coef[2 * t + 1]);
         double m[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) m[r] = c;
@@ -276,6 +276,31 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         // ---- class polynomial on the accumulator fragments, 8 entries at a time ----
         const int row0 = pr * BM + wr * 32 + (lane >> 2);
         const int col0 = pc * BN + wc * 16 + 2 * (lane & 3);
+        // writes the pair (r0, r1) at (row, col + col_shift), (row, col + col_shift + 1); `col` is even
+        auto store_pair = [&](int row, int col, long long col_shift, double r0, double r1) {
+            if (row >= n_rows || col >= n_cols) return;
+            const long long c = col_shift + col;
+            double* dst;
+            bool pair_ok;
+            if (p.out_layout == LSK_OUT_PANEL_MAJOR) {
+                dst = out + (((size_t)(row >> 6) * p.out_kg + (size_t)(c >> 2)) * PANEL + (row & 63)) * 4 + (c & 3);
+                pair_ok = (c & 1) == 0;
+            } else {
+                dst = out + (size_t)row * ld_out + c;
+                pair_ok = vec_ok && ((c & 1) == 0);
+            }
+            if (pair_ok && col + 1 < n_cols) st_cs_f64x2(dst, r0, r1);
+            else {
+                st_cs_f64(dst, r0);
+                if (col + 1 < n_cols) {
+                    const long long c1 = c + 1;
+                    double* d1 = (p.out_layout == LSK_OUT_PANEL_MAJOR)
+                        ? out + (((size_t)(row >> 6) * p.out_kg + (size_t)(c1 >> 2)) * PANEL + (row & 63)) * 4 + (c1 & 3)
+                        : dst + 1;
+                    st_cs_f64(d1, r1);
+                }
+            }
+        };
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             constexpr int R = 8;
@@ -286,36 +311,49 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 const int m = 2 * h + (e >> 2), n = (e >> 1) & 1, i = e & 1;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    double x = p.aff[v][0];
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) x = fma(p.aff[v][1 + f], acc[f][m][n][i], x);
-                    var[v][e] = x;
-                }
-            }
-            if constexpr (EPI == LSK_EPI_CHEB1) epi_cheb1<R>(p, var[0], res);
-            else if constexpr (EPI == LSK_EPI_STAIR2) epi_stair2<R>(p, var[0], var[1], res);
-            else if constexpr (EPI == LSK_EPI_SPARSE) epi_sparse<R, NV>(p, var, res);
-            else {
-                // ORBIT2 keeps a Chebyshev table per entry: run it 2 entries at a time to bound registers
-#pragma unroll
-                for (int e2 = 0; e2 < R; e2 += 2) {
-                    double a1[2] = {var[0][e2], var[0][e2 + 1]}, a2[2] = {var[1][e2], var[1][e2 + 1]}, o[2];
-                    epi_orbit2<2, D>(p, a1, a2, o);
-                    res[e2] = o[0]; res[e2 + 1] = o[1];
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < R; e += 2) {
-                const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
-                const int row = row0 + m * 8, col = col0 + n * 8;
-                if (row < n_rows) {
-                    double* dst = out + (size_t)row * ld_out + col;
-                    const double r0 = p.scale * res[e], r1 = p.scale * res[e + 1];
-                    if (vec_ok && col + 1 < n_cols) st_cs_f64x2(dst, r0, r1);
+                    if constexpr (EPI == LSK_EPI_LINEAR) var[v][e] = acc[0][m][n][i];
                     else {
-                        if (col < n_cols) st_cs_f64(dst, r0);
-                        if (col + 1 < n_cols) st_cs_f64(dst + 1, r1);
+                        double x = p.aff[v][0];
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) x = fma(p.aff[v][1 + f], acc[f][m][n][i], x);
+                        var[v][e] = x;
                     }
+                }
+            }
+            if constexpr (EPI == LSK_EPI_FEAT_CHEB1 || EPI == LSK_EPI_FEAT_SPARSE) {
+                // one output column block per irrep: Phi[i, l * feat_stride + j]
+                int pos = 0;
+                for (int l = 0; l < p.nterms; ++l) {
+                    const int len = p.row_len[l];
+                    if constexpr (EPI == LSK_EPI_FEAT_CHEB1) epi_cheb1<R>(p.coef + pos, len, var[0], res);
+                    else epi_sparse<R, NV>(p.coef + 2 * pos, len, var, res);
+                    pos += len;
+#pragma unroll
+                    for (int e = 0; e < R; e += 2) {
+                        const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
+                        store_pair(row0 + m * 8, col0 + n * 8, (long long)l * p.feat_stride, p.scale * res[e], p.scale * res[e + 1]);
+                    }
+                }
+            } else {
+                if constexpr (EPI == LSK_EPI_CHEB1) epi_cheb1<R>(p.coef, p.nterms, var[0], res);
+                else if constexpr (EPI == LSK_EPI_STAIR2) epi_stair2<R>(p, var[0], var[1], res);
+                else if constexpr (EPI == LSK_EPI_SPARSE) epi_sparse<R, NV>(p.coef, p.nterms, var, res);
+                else if constexpr (EPI == LSK_EPI_LINEAR) {
+#pragma unroll
+                    for (int e = 0; e < R; ++e) res[e] = var[0][e];
+                } else {
+                    // ORBIT2 keeps a Chebyshev table per entry: run it 2 entries at a time to bound registers
+#pragma unroll
+                    for (int e2 = 0; e2 < R; e2 += 2) {
+                        double a1[2] = {var[0][e2], var[0][e2 + 1]}, a2[2] = {var[1][e2], var[1][e2 + 1]}, o[2];
+                        epi_orbit2<2, D>(p, a1, a2, o);
+                        res[e2] = o[0]; res[e2 + 1] = o[1];
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < R; e += 2) {
+                    const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
+                    store_pair(row0 + m * 8, col0 + n * 8, 0, p.scale * res[e], p.scale * res[e + 1]);
                 }
             }
         }
@@ -344,7 +382,10 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
                                  const LskEpilogue* epi, void* out, long long ld_out, void* stream) {
     using namespace lsk;
     if (!A || !B || !out || !epi) return LSK_EARG;
-    if (n_rows < 0 || n_cols < 0 || kg_total <= 0 || ld_out < n_cols) return LSK_ESIZE;
+    if (n_rows < 0 || n_cols < 0 || kg_total <= 0) return LSK_ESIZE;
+    if (epi->out_layout == LSK_OUT_ROW_MAJOR && ld_out < n_cols) return LSK_ESIZE;
+    if (epi->out_layout == LSK_OUT_PANEL_MAJOR && epi->out_kg < 1) return LSK_ESIZE;
+    if (epi->out_layout != LSK_OUT_ROW_MAJOR && epi->out_layout != LSK_OUT_PANEL_MAJOR) return LSK_EARG;
     if (n_rows == 0 || n_cols == 0) return 0;
     if (n_rows > 0x7fffffffLL || n_cols > 0x7fffffffLL) return LSK_ESIZE;
     const LskEpilogue& p = *epi;
@@ -394,6 +435,24 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_SPARSE, 3, 3, 1);
         if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_SPARSE, 4, 4, 1);
         return LSK_EUNSUPPORTED;
+    case LSK_EPI_LINEAR:
+        if (p.nforms == 1 && p.nvars == 1) LSK_GO(LSK_EPI_LINEAR, 1, 1, 1);
+        return LSK_EARG;
+    case LSK_EPI_FEAT_CHEB1:
+    case LSK_EPI_FEAT_SPARSE: {
+        if (p.nterms < 1 || p.nterms > LSK_MAX_ROWS || p.feat_stride < n_cols) return LSK_EARG;
+        int tot = 0;
+        for (int l = 0; l < p.nterms; ++l) { if (p.row_len[l] < 1) return LSK_EARG; tot += p.row_len[l]; }
+        if (p.kind == LSK_EPI_FEAT_CHEB1) {
+            if (tot > LSK_MAX_COEF || p.nvars != 1 || p.nforms != 1) return LSK_ESIZE;
+            LSK_GO(LSK_EPI_FEAT_CHEB1, 1, 1, 1);
+        }
+        if (2 * tot > LSK_MAX_COEF) return LSK_ESIZE;
+        if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_FEAT_SPARSE, 2, 2, 1);
+        if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_FEAT_SPARSE, 3, 3, 1);
+        if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_FEAT_SPARSE, 4, 4, 1);
+        return LSK_EUNSUPPORTED;
+    }
     default:
         return LSK_EARG;
     }

@@ -60,3 +60,88 @@ def pairwise_poly(emb_a: torch.Tensor, emb_b: torch.Tensor, n_rows: int, n_cols:
                    "lsk_pairwise_poly")
         _lib.count_launch()
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# panel-major operands (the layout the pairwise kernel reads and, for feature maps, writes)
+# ----------------------------------------------------------------------------------------------------------
+class PanelMatrix:
+    """A [rows, cols] float64 matrix stored as [row / 64][col / 4][row % 64][col % 4] (rows zero-padded to a
+    multiple of 128, cols to a multiple of 4): one pipeline stage of a 64-row panel is contiguous, and an fp64
+    tensor-core fragment is a conflict-free 256-byte read."""
+
+    def __init__(self, rows: int, cols: int, device, buf: torch.Tensor | None = None):
+        self.rows, self.cols = rows, cols
+        self.kg = max((cols + 3) // 4, 1)
+        self.row_panels = ((rows + 127) // 128) * 2
+        n = self.row_panels * self.kg * 256
+        self.buf = torch.zeros(max(n, 1), dtype=F64, device=device) if buf is None else buf
+
+    @staticmethod
+    def from_dense(dense: torch.Tensor) -> "PanelMatrix":
+        rows, cols = dense.shape
+        pm = PanelMatrix(rows, cols, dense.device)
+        if rows and cols:
+            padded = torch.zeros((pm.row_panels * 64, pm.kg * 4), dtype=F64, device=dense.device)
+            padded[:rows, :cols] = dense
+            pm.buf = padded.view(pm.row_panels, 64, pm.kg, 4).permute(0, 2, 1, 3).contiguous().view(-1)
+        return pm
+
+    def to_dense(self) -> torch.Tensor:
+        v = self.buf[: self.row_panels * self.kg * 256].view(self.row_panels, self.kg, 64, 4).permute(0, 2, 1, 3)
+        return v.reshape(self.row_panels * 64, self.kg * 4)[: self.rows, : self.cols].contiguous()
+
+
+def gram(a: PanelMatrix, b: PanelMatrix, scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """scale * A B^T on the fp64 tensor-core path (the Gram the reference's lazy `MatmulLazyTensor` evaluates to,
+    spectral_kernel.py:125-127, 195-197)."""
+    if a.kg != b.kg:
+        raise ValueError("operands have different inner dimensions")
+    ep = _lib.LskEpilogue()
+    ep.kind, ep.nforms, ep.nvars, ep.nterms = _lib.EPI_LINEAR, 1, 1, 1
+    ep.group_begin[0], ep.group_end[0] = 0, a.kg
+    ep.scale = float(scale)
+    ep.out_layout = _lib.OUT_ROW_MAJOR
+    return pairwise_poly(a.buf, b.buf, a.rows, b.rows, a.kg, ep, out=out)
+
+
+def class_features(plan: GroupPlan, x: torch.Tensor, phases: torch.Tensor, row_scales, panel: bool):
+    """Per-irrep class-function features  Phi[n, l * P + p] = row_scales[l] * Re chi_l(x_n phase_p^{-1})
+    (`make_embedding`, spectral_kernel.py:96-109 / prior_approximation.py:70-83: irrep-major, phase-minor columns).
+    Returns a PanelMatrix (panel=True, ready to be a Gram operand) or a dense [N, L*P] tensor."""
+    _lib.require_cuda()
+    N, P, L = x.shape[0], phases.shape[0], len(plan.irreps)
+    if panel and P % 4:
+        # irrep column blocks must start on a k-group boundary in the panel layout: go through the dense form
+        return PanelMatrix.from_dense(class_features(plan, x, phases, row_scales, panel=False))
+    ea = embed(plan, x, "a")
+    eb = embed(plan, phases, "b")
+    if panel:
+        target = PanelMatrix(N, L * P, x.device)
+        out = target.buf
+    else:
+        target = torch.zeros((N, L * P), dtype=F64, device=x.device)
+        out = target
+    for ep, col_shift in plan.feature_epilogues(row_scales, P):
+        if panel:
+            ep.out_layout, ep.out_kg = _lib.OUT_PANEL_MAJOR, target.kg
+            view = out
+            ld = 0
+        else:
+            ep.out_layout = _lib.OUT_ROW_MAJOR
+            view = out
+            ld = out.stride(0)
+        lib = _lib.load()
+        # column block of this irrep batch starts at col_shift: shift the base pointer (row-major) or the k-group
+        # origin (panel-major; col_shift is a multiple of 4 there because it is l * P and P % 4 == 0 is required)
+        if panel:
+            if col_shift % 4:
+                raise ValueError("panel-major features need the number of phases to be a multiple of 4")
+            base = view.data_ptr() + (col_shift // 4) * 256 * 8
+        else:
+            base = view.data_ptr() + col_shift * 8
+        if N and P:
+            _lib.check(lib.lsk_pairwise_poly(_lib.ptr(ea), _lib.ptr(eb), N, P, plan.kg_total, ctypes.byref(ep),
+                                             ctypes.c_void_p(base), ld, _lib.stream_ptr()), "lsk_pairwise_poly(features)")
+            _lib.count_launch()
+    return target

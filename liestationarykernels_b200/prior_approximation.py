@@ -1,0 +1,57 @@
+"""Prior samplers — drop-in for the reference's `prior_approximation.py:50-123`
+(`RandomPhaseApproximation`, `RandomFourierApproximation`; same attributes `weights`, `phases`, `weights_real`,
+`weights_imag`, same RNG call order in constructors and `resample()`)."""
+from __future__ import annotations
+
+from math import sqrt
+
+import numpy as np
+import torch
+
+from . import ops
+from .space import cuda_device
+from .spectral_kernel import spectral_weights
+
+dtype = torch.float64
+
+
+class RandomPhaseApproximation(torch.nn.Module):
+    """f(x) = Phi(x) w,  w ~ N(0, I_{L*P}),  Phi scaled by sqrt(|sigma^2| a_l / norm / P)  (prior_approximation.py:50-92)."""
+
+    def __init__(self, kernel, phase_order=1000):
+        super().__init__()
+        self.kernel = kernel
+        self.approx_order = len(self.kernel.manifold.lb_eigenspaces)
+        self.phase_order = phase_order
+        self.weights = self.sample_weights()
+        self.phases = self.sample_phases()
+
+    def sample_weights(self):
+        return torch.randn(self.phase_order * self.approx_order, device=cuda_device(), dtype=dtype)
+
+    def sample_phases(self):
+        return self.kernel.manifold.rand(self.phase_order)
+
+    def resample(self):
+        self.weights = self.sample_weights()
+        self.phases = self.sample_phases()
+
+    def _row_scales(self):
+        k = self.kernel
+        a = spectral_weights(k.measure, k.manifold)
+        var = abs(float(k.measure.variance[0]))
+        return np.sqrt(var * a) / sqrt(float(k.normalizer)) / sqrt(self.phase_order)
+
+    def make_embedding(self, x):
+        return self.kernel.manifold._phase_features(x, self.phases, self._row_scales(), panel=False)
+
+    def forward(self, x):
+        feats = self.kernel.manifold._phase_features(x, self.phases, self._row_scales(), panel=True)
+        w = ops.PanelMatrix.from_dense(self.weights.reshape(1, -1))
+        return ops.gram(feats, w)[:, 0]
+
+    def _cov(self, x, y):
+        scales = self._row_scales()
+        fx = self.kernel.manifold._phase_features(x, self.phases, scales, panel=True)
+        fy = self.kernel.manifold._phase_features(y, self.phases, scales, panel=True)
+        return ops.gram(fx, fy)

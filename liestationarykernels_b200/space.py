@@ -140,6 +140,12 @@ class CompactLieGroup(AbstractManifold, ABC):
     def pairwise_embed(self, x, y):
         return self.torus_representative(self.pairwise_diff(x, y))
 
+    def _phase_features(self, x, phases, row_scales, panel):
+        """Phi[n, l*P + p] = row_scales[l] * d_l * Re chi_l(phase_p x_n^{-1})  (space.py:80-85 + 259-262 fused)."""
+        from . import ops
+        scales = np.asarray(row_scales, dtype=np.float64) * self._dims
+        return ops.class_features(self.plan, x, phases, scales, panel)
+
     def _reference_table(self, signature):
         from . import characters as ch
         cs, ms = ch.reference_table_entry(self.family, self.n, tuple(signature))

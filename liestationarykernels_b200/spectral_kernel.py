@@ -79,5 +79,49 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         return self._ep_cache["ep"]
 
 
+class RandomPhaseKernel(AbstractSpectralKernel):
+    """Feature-map approximation with random phases (spectral_kernel.py:78-127):
+       Phi[n, l*P + p] = sqrt(a_l / P) * Re phase_function_l(phase_p, x_n),   k = |sigma^2| / norm * Phi_x Phi_y^T."""
+
+    def __init__(self, measure, manifold, phase_order=100):
+        super().__init__(measure, manifold)
+        self.approx_order = manifold.order
+        self.phase_order = phase_order
+        self.phases = self.sample_phases()
+        point = self.manifold.rand()
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def compute_normalizer(self):
+        point = self.manifold.id
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def sample_phases(self):
+        return self.manifold.rand(self.phase_order)
+
+    def _row_scales(self, extra=1.0):
+        a = spectral_weights(self.measure, self.manifold)
+        return np.sqrt(a * extra) / np.sqrt(self.phase_order)
+
+    def _features(self, x, scales, panel):
+        return self.manifold._phase_features(x, self.phases, scales, panel)
+
+    def make_embedding(self, x):
+        """[N, L*P] float64, irrep-major / phase-minor columns (spectral_kernel.py:96-109)."""
+        return self._features(x, self._row_scales(), panel=False)
+
+    def forward(self, x, y=None, normalize=True):
+        if y is None:
+            y = x
+        if self.training:
+            if normalize:
+                self.compute_normalizer()
+        scales = self._row_scales()
+        fx = self._features(x, scales, panel=True)
+        fy = fx if y is x else self._features(y, scales, panel=True)
+        scale = float(torch.abs(self.measure.variance[0]).item() / float(self.normalizer)) if normalize else 1.0
+        from .lazy import LazyGram
+        return LazyGram(fx, fy, scale)
+
+
 # north_star spelling
 EigenSumKernel = EigenbasisSumKernel
