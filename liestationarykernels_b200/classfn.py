@@ -273,6 +273,37 @@ class GroupPlan:
             yield ep, start * stride
             start = stop
 
+    def collapsed_row_epilogue(self, weights, scale: float):
+        """One output row = sum_l weights[l] chi_l, in the per-row encoding of the FEAT_* epilogues (used by the
+        homogeneous-space pair kernel, where the polynomial is evaluated once per subgroup sample)."""
+        from ._lib import EPI_FEAT_CHEB1, EPI_FEAT_SPARSE
+        coef = _dot_long(np.asarray(weights, dtype=np.float64), self.M)
+        ep = self._base_epilogue()
+        ep.scale = float(scale)
+        ep.nterms = 1
+        ep.feat_stride = 0
+        if self.kind == "cheb1":
+            if len(coef) > MAX_COEF:
+                raise ValueError("order too large")
+            ep.kind = EPI_FEAT_CHEB1
+            ep.row_len[0] = len(coef)
+            for i, c in enumerate(coef):
+                ep.coef[i] = c
+            return ep
+        expo = self.monos if self.kind == "rank2" else self.sparse_expo
+        keep = [(c, e) for c, e in zip(coef, expo) if c != 0.0]
+        if 2 * len(keep) > MAX_COEF:
+            raise ValueError("too many polynomial terms (%d) for the homogeneous-space kernel" % len(keep))
+        ep.kind = EPI_FEAT_SPARSE
+        ep.row_len[0] = len(keep)
+        for t, (c, e) in enumerate(keep):
+            packed = 0
+            for j, ej in enumerate(e):
+                packed |= int(ej) << (8 * j)
+            ep.coef[2 * t] = c
+            ep.coef[2 * t + 1] = np.array([packed], dtype=np.uint64).view(np.float64)[0]
+        return ep
+
     # ------------------------------------------------------------------ fast-form safety check (rank 2)
     def _probe(self):
         if getattr(self, "_probe_cache", None) is not None:

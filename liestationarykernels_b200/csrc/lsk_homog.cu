@@ -1,0 +1,293 @@
+// Homogeneous spaces M = SO(n)/H (Stiefel, Grassmannian, oriented Grassmannian).
+//
+// (1) lsk_lift_frames: the lift M -> G of `Stiefel.M_to_G` (spaces/stiefel.py:38-48; identical copies in
+//     spaces/grassmannian.py:74-85,120-130): complete Householder QR with LAPACK's conventions
+//     (beta = -sign(alpha) * norm, v_0 = 1, Q = H_0 H_1 ... H_{m-1}), columns scaled by diag(R), the row-sign
+//     check of the reference, and the determinant fix on the last column.  With a finite number of H samples the
+//     kernel value depends on which orthonormal completion is chosen, so this is reproduced
+//     exactly rather than replaced by any other completion.
+// (2) lsk_homog_pairs: for every pair (x_i, y_j) and every subgroup sample h_k the element
+//         g_ijk = lift(x_i)^T lift(y_j) h_k^T                (space.py:125-135)
+//     is formed in registers, its conjugation invariants tr g, tr g^2 are taken, the class polynomials are
+//     evaluated and averaged over k (AveragedLieGroupCharacter.forward, space.py:273-275).  One launch produces
+//     either per-irrep features Phi[i, l*stride + j] or, with a single collapsed polynomial, the covariance
+//     entry itself.  Nothing of size N*M*A is ever stored (the reference materialises [N*M*A, n, n]).
+#include "lsk_common.cuh"
+#include "lsk_pairwise.cuh"
+
+namespace lsk {
+
+// ------------------------------------------------------------------------------------------------------------
+// lift
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+lift_kernel(const double* __restrict__ x, long long num, int n, int m, double* __restrict__ out, int* __restrict__ bad) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num) return;
+    double a[8][8], q[8][8], rd[8], v[8], tau[8];
+    const double* xb = x + b * n * m;
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < m; ++c) a[r][c] = xb[r * m + c];
+    // ---- Householder QR (dgeqr2 / dlarfg) ----
+    for (int j = 0; j < m; ++j) {
+        const double alpha = a[j][j];
+        double ss = 0.0;
+        for (int r = j + 1; r < n; ++r) ss += a[r][j] * a[r][j];
+        if (ss == 0.0) {
+            tau[j] = 0.0;
+            rd[j] = alpha;
+        } else {
+            const double nrm = sqrt(alpha * alpha + ss);
+            const double beta = alpha >= 0.0 ? -nrm : nrm;
+            tau[j] = (beta - alpha) / beta;
+            const double sc = 1.0 / (alpha - beta);
+            for (int r = j + 1; r < n; ++r) a[r][j] *= sc;        // v (v_j = 1 implicit) stored below the diagonal
+            rd[j] = beta;
+            for (int c = j + 1; c < m; ++c) {                     // apply H_j to the trailing columns
+                double w = a[j][c];
+                for (int r = j + 1; r < n; ++r) w += a[r][j] * a[r][c];
+                w *= tau[j];
+                a[j][c] -= w;
+                for (int r = j + 1; r < n; ++r) a[r][c] -= a[r][j] * w;
+            }
+        }
+    }
+    // ---- Q = H_0 ... H_{m-1} applied to the identity (dorg2r order: last reflector first) ----
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) q[r][c] = (r == c) ? 1.0 : 0.0;
+    for (int j = m - 1; j >= 0; --j) {
+        if (tau[j] == 0.0) continue;
+        v[j] = 1.0;
+        for (int r = j + 1; r < n; ++r) v[r] = a[r][j];
+        for (int c = j; c < n; ++c) {
+            double w = 0.0;
+            for (int r = j; r < n; ++r) w += v[r] * q[r][c];
+            w *= tau[j];
+            for (int r = j; r < n; ++r) q[r][c] -= v[r] * w;
+        }
+    }
+    // ---- stiefel.py:40-46 ----
+    for (int c = 0; c < m; ++c)
+        for (int r = 0; r < n; ++r) q[r][c] *= rd[c];             // g = g * r_diag  (columns; complement scaled by 1)
+    bool mismatch = false;
+    for (int r = 0; r < n; ++r) {
+        bool close = true;
+        for (int c = 0; c < m; ++c) {
+            const double ref = xb[r * m + c];
+            close = close && (fabs(q[r][c] - ref) <= 1e-8 + 1e-5 * fabs(ref));   // torch.isclose defaults
+        }
+        if (!close)
+            for (int c = 0; c < n; ++c) q[r][c] = -q[r][c];
+    }
+    // determinant by Gaussian elimination with partial pivoting (only its sign is used)
+    double lu[8][8];
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) lu[r][c] = q[r][c];
+    double det = 1.0;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (fabs(lu[r][c]) > fabs(lu[piv][c])) piv = r;
+        if (piv != c) {
+            for (int k = 0; k < n; ++k) { const double t = lu[c][k]; lu[c][k] = lu[piv][k]; lu[piv][k] = t; }
+            det = -det;
+        }
+        det *= lu[c][c];
+        if (lu[c][c] == 0.0) break;
+        for (int r = c + 1; r < n; ++r) {
+            const double f = lu[r][c] / lu[c][c];
+            for (int k = c + 1; k < n; ++k) lu[r][k] -= f * lu[c][k];
+        }
+    }
+    const double sgn = det > 0.0 ? 1.0 : (det < 0.0 ? -1.0 : 0.0);
+    for (int r = 0; r < n; ++r) q[r][n - 1] *= sgn;
+    // the reference asserts that the lift reproduces x (stiefel.py:47, torch.allclose defaults)
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < m; ++c) {
+            const double ref = xb[r * m + c];
+            if (!(fabs(q[r][c] - ref) <= 1e-8 + 1e-5 * fabs(ref))) mismatch = true;
+        }
+    if (mismatch) atomicAdd(bad, 1);
+    double* ob = out + b * n * n;
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) ob[r * n + c] = q[r][c];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pair kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ double eval_sparse_row(const double* coef, int nterms, const double (&v)[NV]) {
+    double acc = 0.0;
+    for (int t = 0; t < nterms; ++t) {
+        double m = coef[2 * t];
+        const unsigned long long e = (unsigned long long)__double_as_longlong(coef[2 * t + 1]);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int ei = (int)((e >> (8 * i)) & 0xffu);
+            for (int k = 0; k < ei; ++k) m *= v[i];
+        }
+        acc += m;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ double eval_cheb_row(const double* coef, int nterms, double x) {
+    double b1 = 0.0, b2 = 0.0;
+    const double x2 = 2.0 * x;
+    for (int k = nterms - 1; k >= 1; --k) {
+        const double t = fma(x2, b1, coef[k] - b2);
+        b2 = b1;
+        b1 = t;
+    }
+    return fma(x, b1, coef[0] - b2);
+}
+
+// N_: matrix size (3 or 5);  rank = N_ / 2 invariants.  blockDim = (32, 8): x = column j (fastest), y = row i.
+template <int N_>
+__global__ void __launch_bounds__(256)
+homog_pair_kernel(const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ h,
+                  int n_rows, int n_cols, int n_avg, double* __restrict__ out, long long ld_out,
+                  const __grid_constant__ LskEpilogue p)
+{
+    constexpr int RANK = N_ / 2;
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= n_rows || j >= n_cols) return;
+    double M[N_][N_];
+    {
+        double xi[N_][N_], yj[N_][N_];
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                xi[a][b] = gx[(size_t)i * N_ * N_ + a * N_ + b];
+                yj[a][b] = gy[(size_t)j * N_ * N_ + a * N_ + b];
+            }
+        // M = x_i^T y_j   (pairwise_diff(..., reverse=True), space.py:125-129);  with p.reserved & 1 the roles are
+        // swapped, M = y_j^T x_i: feature maps pair (phase_j, point_i) as pairwise_embed(phases, x) does
+        const bool swap = (p.reserved & 1) != 0;
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < N_; ++c) s = swap ? fma(yj[c][a], xi[c][b], s) : fma(xi[c][a], yj[c][b], s);
+                M[a][b] = s;
+            }
+    }
+    const int rows = p.nterms;
+    double sum[LSK_MAX_ROWS];
+#pragma unroll
+    for (int l = 0; l < LSK_MAX_ROWS; ++l) sum[l] = 0.0;
+
+    for (int k = 0; k < n_avg; ++k) {
+        const double* hk = h + (size_t)k * N_ * N_;
+        double form[RANK];
+        if constexpr (RANK == 1) {
+            double t1 = 0.0;                                     // tr(M h^T) = <M, h>_F
+#pragma unroll
+            for (int a = 0; a < N_; ++a)
+#pragma unroll
+                for (int b = 0; b < N_; ++b) t1 = fma(M[a][b], __ldg(hk + a * N_ + b), t1);
+            form[0] = t1;
+        } else {
+            double G[N_][N_];                                    // G = M h_k^T
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                double hb[N_];
+#pragma unroll
+                for (int c = 0; c < N_; ++c) hb[c] = __ldg(hk + b * N_ + c);
+#pragma unroll
+                for (int a = 0; a < N_; ++a) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N_; ++c) s = fma(M[a][c], hb[c], s);
+                    G[a][b] = s;
+                }
+            }
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int a = 0; a < N_; ++a) {
+                t1 += G[a][a];
+#pragma unroll
+                for (int b = 0; b < N_; ++b) t2 = fma(G[a][b], G[b][a], t2);
+            }
+            form[0] = t1;
+            form[1] = 0.5 * (t1 * t1 - t2);                      // e_2(g)
+        }
+        double var[RANK];
+#pragma unroll
+        for (int v = 0; v < RANK; ++v) {
+            double xv = p.aff[v][0];
+#pragma unroll
+            for (int f = 0; f < RANK; ++f) xv = fma(p.aff[v][1 + f], form[f], xv);
+            var[v] = xv;
+        }
+        int pos = 0;
+#pragma unroll
+        for (int l = 0; l < LSK_MAX_ROWS; ++l) {
+            if (l < rows) {
+                const int len = p.row_len[l];
+                if constexpr (RANK == 1) sum[l] += eval_cheb_row(p.coef + pos, len, var[0]);
+                else sum[l] += eval_sparse_row<RANK>(p.coef + 2 * pos, len, var);
+                pos += len;
+            }
+        }
+    }
+    const double inv_avg = p.scale / (double)n_avg;
+#pragma unroll
+    for (int l = 0; l < LSK_MAX_ROWS; ++l) {
+        if (l < rows) {
+            const long long c = (long long)l * p.feat_stride + j;
+            double* dst = (p.out_layout == LSK_OUT_PANEL_MAJOR)
+                ? out + (((size_t)(i >> 6) * p.out_kg + (size_t)(c >> 2)) * PANEL + (i & 63)) * 4 + (c & 3)
+                : out + (size_t)i * ld_out + c;
+            *dst = sum[l] * inv_avg;
+        }
+    }
+}
+
+}  // namespace lsk
+
+extern "C" int lsk_lift_frames(const void* x, long long num, int n, int m, void* out, void* bad_count, void* stream) {
+    using namespace lsk;
+    if (!x || !out || !bad_count) return LSK_EARG;
+    if (num < 0 || n < 2 || n > 8 || m < 1 || m >= n) return LSK_ESIZE;
+    if (num == 0) return 0;
+    const long long blocks = (num + 127) / 128;
+    lift_kernel<<<(unsigned)blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<const double*>(x), num, n, m, static_cast<double*>(out), static_cast<int*>(bad_count));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const void* h_samples, long long n_rows,
+                               long long n_cols, int n, int n_avg, const LskEpilogue* epi, void* out, long long ld_out,
+                               void* stream) {
+    using namespace lsk;
+    if (!lifted_x || !lifted_y || !h_samples || !epi || !out) return LSK_EARG;
+    if (n_rows < 0 || n_cols < 0 || n_avg < 1) return LSK_ESIZE;
+    if (n_rows == 0 || n_cols == 0) return 0;
+    const LskEpilogue& p = *epi;
+    if (p.nterms < 1 || p.nterms > LSK_MAX_ROWS) return LSK_EARG;
+    if (p.out_layout == LSK_OUT_ROW_MAJOR && ld_out < n_cols) return LSK_ESIZE;
+    if (p.out_layout == LSK_OUT_PANEL_MAJOR && p.out_kg < 1) return LSK_ESIZE;
+    int tot = 0;
+    for (int l = 0; l < p.nterms; ++l) { if (p.row_len[l] < 1) return LSK_EARG; tot += p.row_len[l]; }
+    dim3 block(32, 8), grid((unsigned)((n_cols + 31) / 32), (unsigned)((n_rows + 7) / 8));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double* gx = static_cast<const double*>(lifted_x);
+    const double* gy = static_cast<const double*>(lifted_y);
+    const double* hh = static_cast<const double*>(h_samples);
+    double* o = static_cast<double*>(out);
+    if (n == 3) {
+        if (p.kind != LSK_EPI_FEAT_CHEB1 || tot > LSK_MAX_COEF) return LSK_EARG;
+        homog_pair_kernel<3><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+    } else if (n == 5) {
+        if (p.kind != LSK_EPI_FEAT_SPARSE || 2 * tot > LSK_MAX_COEF) return LSK_EARG;
+        homog_pair_kernel<5><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+    } else {
+        return LSK_EUNSUPPORTED;
+    }
+    return (int)cudaGetLastError();
+}

@@ -1,2 +1,3 @@
 from .so import SO
 from .su import SU
+from .homogeneous import Stiefel, Grassmannian, OrientedGrassmannian
