@@ -19,7 +19,7 @@ MAX_COEF = 400
 MAX_ROWS = 24
 
 EPI_CHEB1, EPI_STAIR2, EPI_ORBIT2, EPI_SPARSE, EPI_LINEAR, EPI_FEAT_CHEB1, EPI_FEAT_SPARSE = 1, 2, 3, 4, 5, 6, 7
-OUT_ROW_MAJOR, OUT_PANEL_MAJOR = 0, 1
+OUT_ROW_MAJOR, OUT_PANEL_MAJOR, FEAT_COMPLEX = 0, 1, 2
 
 
 class LskEpilogue(ctypes.Structure):
@@ -59,6 +59,14 @@ _PROTOTYPES = {
     "lsk_homog_pairs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong,
                                        ctypes.c_int, ctypes.c_int, ctypes.POINTER(LskEpilogue), ctypes.c_void_p,
                                        ctypes.c_longlong, ctypes.c_void_p]),
+    "lsk_hyp_features": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+    "lsk_spd_features": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+    "lsk_small_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "lsk_pairwise_poly": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
                                          ctypes.POINTER(LskEpilogue), ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
 }

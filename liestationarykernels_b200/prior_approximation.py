@@ -55,3 +55,37 @@ class RandomPhaseApproximation(torch.nn.Module):
         fx = self.kernel.manifold._phase_features(x, self.phases, scales, panel=True)
         fy = self.kernel.manifold._phase_features(y, self.phases, scales, panel=True)
         return ops.gram(fx, fy)
+
+
+class RandomFourierApproximation(torch.nn.Module):
+    """f(x) = (Re F w_re - Im F w_im) sqrt(|sigma^2|) / sqrt(norm)   (prior_approximation.py:95-123)."""
+
+    def __init__(self, kernel):
+        super().__init__()
+        self.kernel = kernel
+        self.weights_real = self.sample_weights()
+        self.weights_imag = self.sample_weights()
+
+    def sample_weights(self):
+        return torch.randn(self.kernel.manifold.order, dtype=dtype, device=cuda_device())
+
+    def resample(self):
+        self.weights_real = self.sample_weights()
+        self.weights_imag = self.sample_weights()
+        self.kernel.manifold.generate_lb_eigenspaces(self.kernel.measure)
+
+    def _scale(self):
+        k = self.kernel
+        return sqrt(abs(float(k.measure.variance[0]))) / sqrt(float(k.normalizer))
+
+    def forward(self, x):
+        m = self.kernel.manifold
+        psi = m._features(m.to_group(x), m.lb_eigenspaces, self._scale(), "panel")
+        w = torch.cat((self.weights_real, -self.weights_imag)).reshape(1, -1)
+        return ops.gram(psi, ops.PanelMatrix.from_dense(w))[:, 0]
+
+    def _cov(self, x, y):
+        m = self.kernel.manifold
+        px = m._features(m.to_group(x), m.lb_eigenspaces, self._scale(), "panel")
+        py = m._features(m.to_group(y), m.lb_eigenspaces, self._scale(), "panel")
+        return ops.gram(px, py)

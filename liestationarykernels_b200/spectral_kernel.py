@@ -123,5 +123,75 @@ class RandomPhaseKernel(AbstractSpectralKernel):
         return LazyGram(fx, fy, scale)
 
 
-# north_star spelling
+def _rff_scale(kernel, normalize):
+    if not normalize:
+        return 1.0
+    return (abs(float(kernel.measure.variance[0])) / float(kernel.normalizer)) ** 0.5
+
+
+class RandomFourierFeatureKernel(AbstractSpectralKernel):
+    """Random Fourier features on a non-compact symmetric space (spectral_kernel.py:164-197):
+       Psi = sqrt(|sigma^2| / norm) [Re F, Im F],  k = Psi_x Psi_y^T  (returned lazily)."""
+
+    def __init__(self, measure, manifold):
+        super().__init__(measure, manifold)
+        manifold.generate_lb_eigenspaces(measure)
+        point = self.manifold.id
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def compute_normalizer(self):
+        point = self.manifold.id
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def forward(self, x, y=None, normalize=True):
+        if self.training:
+            self.manifold.generate_lb_eigenspaces(self.measure)
+            if normalize:
+                self.compute_normalizer()
+        if y is None:
+            y = x
+        manifold = self.manifold
+        s = _rff_scale(self, normalize)
+        px = manifold._features(manifold.to_group(x), manifold.lb_eigenspaces, s, "panel")
+        py = px if y is x else manifold._features(manifold.to_group(y), manifold.lb_eigenspaces, s, "panel")
+        from .lazy import LazyGram
+        return LazyGram(px, py, 1.0)
+
+
+class RandomSpectralKernel(AbstractSpectralKernel):
+    """Pairwise form (spectral_kernel.py:130-161): k(x, y) = Re sum_k F_k(x y^{-1}) conj(F_k(id)).
+    Like the reference this needs O(N*M*m) feature evaluations; it exists for API parity (the reference's tests use it
+    to cross-check the feature-map kernel on small inputs)."""
+
+    def __init__(self, measure, manifold):
+        super().__init__(measure, manifold)
+        manifold.generate_lb_eigenspaces(measure)
+        point = self.manifold.rand()
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def compute_normalizer(self):
+        point = self.manifold.rand()
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def forward(self, x, y=None, normalize=True):
+        if self.training:
+            self.manifold.generate_lb_eigenspaces(self.measure)
+            if normalize:
+                self.compute_normalizer()
+        if y is None:
+            y = x
+        manifold = self.manifold
+        x_, y_ = manifold.to_group(x), manifold.to_group(y)
+        diff = manifold.pairwise_diff(x_, y_)
+        f = manifold.lb_eigenspaces
+        p_diff = manifold._features(diff, f, 1.0, "panel")
+        p_id = manifold._features(manifold.to_group(manifold.id) if manifold.id.dim() == 3 else manifold.id, f, 1.0, "panel")
+        cov = ops.gram(p_diff, p_id)[:, 0].view(x.size()[0], y.size()[0])
+        if normalize:
+            return self.measure.variance[0].detach() * cov / self.normalizer
+        return cov
+
+
+# north_star spellings
 EigenSumKernel = EigenbasisSumKernel
+RandomFourierKernel = RandomFourierFeatureKernel

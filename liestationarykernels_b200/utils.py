@@ -30,3 +30,12 @@ def lazy_property(fn):
             setattr(self, attr, fn(self))
         return getattr(self, attr)
     return _lazy
+
+
+def GOE_sampler(num_samples, n):
+    """Spectra of GOE matrices (utils.py:7-11): same torch RNG call as the reference; eigvalsh stays a library call
+    (setup-time, m small matrices)."""
+    from .space import cuda_device
+    s = torch.randn(num_samples, n, n, device=cuda_device(), dtype=torch.float64)
+    s = (s + torch.transpose(s, -2, -1)) / 2
+    return torch.linalg.eigvalsh(s, UPLO='U')

@@ -1,0 +1,87 @@
+"""GPU parity for H^n / SPD(n): spherical-function features, RandomFourierFeatureKernel, RandomFourierApproximation,
+against golden outputs of the real reference with injected spectral samples, shifts and weights."""
+import pytest
+import torch
+
+from conftest import load_golden, scaled_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+CASES = ["rff_h3_matern", "rff_h3_heat", "rff_h2_heat", "rff_h5_matern", "rff_spd3_matern", "rff_spd3_heat",
+         "rff_spd2_heat", "rff_spd4_heat"]
+
+
+def _measure(spec):
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure, SqExpSpectralMeasure
+    if spec["kind"] == "matern":
+        return MaternSpectralMeasure(spec["dim"], spec["lengthscale"], spec["nu"], spec.get("variance", 1.0))
+    return SqExpSpectralMeasure(spec["dim"], spec["lengthscale"], spec.get("variance", 1.0))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_noncompact_golden(name):
+    from liestationarykernels_b200 import spaces
+    from liestationarykernels_b200.spaces.noncompact import _SphericalFunctions
+    from liestationarykernels_b200.spectral_kernel import RandomFourierFeatureKernel, RandomSpectralKernel
+    from liestationarykernels_b200.prior_approximation import RandomFourierApproximation
+    g = load_golden(name)
+    space = getattr(spaces, g["cls"])(g["n"], order=g["order"])
+    meas = _measure(g["measure"])
+    torch.manual_seed(0)
+    kern = RandomFourierFeatureKernel(meas, space)
+    kern.eval()
+    assert space.lb_eigenspaces.exp.lmd.shape == g["lmd"].shape
+    assert space.lb_eigenspaces.exp.shift.shape == g["shift"].shape
+    # inject the reference's spectral samples and shifts; the c-function is recomputed by our code
+    lmd, shift = g["lmd"].cuda(), g["shift"].cuda()
+    coeff = space.c_function(lmd) if g["cls"] == "HyperbolicSpace" else space.c_function_tanh(lmd)
+    assert scaled_err(coeff.cpu(), g["coeff"]) < 1e-13
+    space.lb_eigenspaces = _SphericalFunctions(lmd, shift, space, coeff)
+    x, y = g["x"].cuda(), g["y"].cuda()
+    with torch.no_grad():
+        feats = space.lb_eigenspaces(space.to_group(x)).cpu()
+        assert feats.dtype == torch.complex128 and feats.shape == g["features"].shape
+        assert scaled_err(feats, g["features"]) < TOL
+        kern.compute_normalizer()
+        assert abs(float(kern.normalizer) / float(g["normalizer"]) - 1) < 1e-12
+        gram = kern(x, y).evaluate().cpu()
+        assert scaled_err(gram, g["gram"]) < TOL
+        sampler = RandomFourierApproximation(kern)
+        sampler.weights_real, sampler.weights_imag = g["w_re"].cuda(), g["w_im"].cuda()
+        assert scaled_err(sampler(x).cpu(), g["sample"]) < TOL
+        assert scaled_err(sampler._cov(x, y).cpu(), g["cov"]) < TOL
+
+
+def test_spd_to_group_and_inverse():
+    from liestationarykernels_b200.spaces import SymmetricPositiveDefiniteMatrices
+    space = SymmetricPositiveDefiniteMatrices(3, order=8)
+    torch.manual_seed(0)
+    x = space.rand(200)
+    u = space.to_group(x)
+    # Wishart-type samples can be badly conditioned; both factorizations are backward stable, so compare residuals
+    assert torch.allclose(u.transpose(-1, -2) @ u, x, rtol=1e-13, atol=1e-13)
+    assert torch.equal(u, torch.triu(u))
+    ref = torch.linalg.cholesky(x, upper=True)
+    assert ((u - ref).abs().amax(dim=(1, 2)) / ref.abs().amax(dim=(1, 2))).median().item() < 1e-14
+    eye = torch.eye(3, dtype=torch.float64, device='cuda')
+    assert ((space.inv(x) @ x - eye).abs().amax(dim=(1, 2)) / torch.linalg.cond(x)).max().item() < 1e-14
+
+
+def test_hyperbolic_rff_and_pairwise_kernels_agree():
+    """reference tests/hyperbolic.py:27-38 (Monte-Carlo, atol 5e-2): feature-map kernel vs pairwise spectral kernel"""
+    from liestationarykernels_b200.spaces import HyperbolicSpace
+    from liestationarykernels_b200.spectral_kernel import RandomFourierFeatureKernel, RandomSpectralKernel
+    from liestationarykernels_b200.spectral_measure import SqExpSpectralMeasure
+    torch.manual_seed(0)
+    space = HyperbolicSpace(3, order=400000)
+    meas = SqExpSpectralMeasure(3, 1.0)
+    k1 = RandomFourierFeatureKernel(meas, space)
+    k1.eval()
+    k2 = RandomSpectralKernel(meas, space)
+    k2.eval()
+    x = space.rand(10) * 0.6
+    with torch.no_grad():
+        a, b = k1(x, x).evaluate(), k2(x, x)
+    assert torch.allclose(torch.diagonal(b), torch.ones(10, dtype=torch.float64, device="cuda"), atol=1e-9)
+    assert (a - b).abs().max().item() < 0.1, (a - b).abs().max().item()
