@@ -1,0 +1,122 @@
+/* liblsk — C ABI of the B200-native hot path of LieStationaryKernels.
+ *
+ * The reference (imbirik/LieStationaryKernels) is pure Python and has no FFI; the boundary a maintainer binds is
+ * this header (ctypes stub: INTEGRATION.md).  Every entry point
+ *   - is `extern "C"`, takes plain pointers and sizes, returns int: 0 ok, < 0 argument error (LSK_E*), > 0 cudaError_t;
+ *   - takes DEVICE pointers for bulk data (contiguous, row-major float64 unless stated; complex128 = interleaved re,im),
+ *     caller-owned, 16-byte aligned; small descriptors (`LskEpilogue`, int arrays) are HOST pointers read during the call;
+ *   - launches asynchronously on the `cudaStream_t` passed as `void* stream` (NULL = default stream);
+ *   - allocates nothing that outlives the call and keeps no mutable global state (safe from several host threads on
+ *     distinct streams).
+ * "reference" citations are paths below /root/reference/src/lie_stationary_kernels/.
+ */
+#ifndef LSK_H
+#define LSK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSK_EARG         (-1)   /* invalid argument            */
+#define LSK_ESIZE        (-2)   /* size out of supported range */
+#define LSK_EUNSUPPORTED (-3)   /* configuration not compiled  */
+
+#define LSK_MAX_FORMS 4
+#define LSK_MAX_VARS  4
+#define LSK_MAX_COEF  400
+#define LSK_MAX_ROWS  24
+
+/* epilogue kinds */
+#define LSK_EPI_CHEB1       1   /* rank 1: sum_k coef[k] T_k(var0)  (Clenshaw)                                   */
+#define LSK_EPI_STAIR2      2   /* rank 2: sum_b var1^b sum_a C[b][a] var0^a  (nested Horner, fast form)         */
+#define LSK_EPI_ORBIT2      3   /* rank 2: sum_ab W[a][b] T_a(c1) T_b(c2), c1+c2 = var0, c1 c2 = var1 (robust)   */
+#define LSK_EPI_SPARSE      4   /* any  : sum_t coef[2t] prod_v var_v^e_tv, e packed 8 bits each in coef[2t+1]  */
+#define LSK_EPI_LINEAR      5   /* out = scale * form_0  (Gram of two feature maps)                              */
+#define LSK_EPI_FEAT_CHEB1  6   /* per-irrep rows, rank 1 (row l: row_len[l] Chebyshev coefficients)             */
+#define LSK_EPI_FEAT_SPARSE 7   /* per-irrep rows, any rank (row l: row_len[l] sparse terms)                     */
+
+/* output layouts */
+#define LSK_OUT_ROW_MAJOR   0   /* out[i * ld_out + j]                                                            */
+#define LSK_OUT_PANEL_MAJOR 1   /* [i / 64][j / 4][i % 64][j % 4]: the operand layout the pairwise kernel reads   */
+#define LSK_FEAT_COMPLEX    2   /* complex128 [N, m] interleaved (feature kernels only)                           */
+
+/* One pairwise problem.  nforms bilinear forms u_f(i,j) = sum_{k in 4*[group_begin_f, group_end_f)} A[i,k] B[j,k],
+ *   var_v = aff[v][0] + sum_f aff[v][1+f] u_f,     out[i,j] = scale * P(var_0 .. var_{nvars-1}).
+ * Passed by value to the kernel: the coefficient table is read from the constant bank. */
+typedef struct LskEpilogue {
+    int32_t kind;
+    int32_t nforms;
+    int32_t nvars;
+    int32_t nterms;                      /* CHEB1 #coef; STAIR2 #rows; ORBIT2 matrix size; SPARSE #terms; FEAT_* #irreps */
+    int32_t group_begin[LSK_MAX_FORMS];
+    int32_t group_end[LSK_MAX_FORMS];
+    int32_t row_len[LSK_MAX_ROWS];
+    int32_t out_layout;
+    int32_t out_kg;                      /* PANEL_MAJOR: k-groups (4 columns) per output row */
+    int32_t feat_stride;                 /* FEAT_*: column offset between irreps (= number of phases) */
+    int32_t reserved;                    /* lsk_homog_pairs: bit 0 = pair (y_j, x_i) instead of (x_i, y_j) */
+    double scale;
+    double aff[LSK_MAX_VARS][1 + LSK_MAX_FORMS];
+    double coef[LSK_MAX_COEF];
+} LskEpilogue;
+
+int lsk_version(void);
+
+/* Number of doubles of the panel-major embedding buffer for `num` points and `kg_total` k-groups. */
+long long lsk_embed_buffer_doubles(long long num, int kg_total);
+
+/* Per-point compound-matrix embeddings (k = 1..3) of SO(n)/SU(n) elements, panel-major output.
+ * Replaces operand preparation of CompactLieGroup.pairwise_diff: inv + cartesian_prod + bmm (reference space.py:62-78,
+ * utils.py:40-52, spaces/so.py:124-127, spaces/su.py:79-82).
+ * x: [num, n, n] float64 (is_complex = 0) or complex128 (is_complex = 1).  wedge/part/group_begin: host int[nseg].
+ * part: 0 real; 1 complex (re,im); 2 complex (re,im) [second operand, real form]; 3 complex (-im,re) [imaginary form]. */
+int lsk_embed_points(const void* x, long long num, int n, int is_complex, int nseg, const int* wedge, const int* part,
+                     const int* group_begin, int kg_total, void* out, void* stream);
+
+/* Fused pairwise kernel: bilinear forms on the fp64 tensor-core path + class-polynomial epilogue + store.
+ * Replaces, for all N*M pairs, pairwise_embed + the character loop + the weighted sum:
+ *   reference space.py:80-85, spaces/so.py:136-168,288-293, spaces/su.py:91-92,175-179, spectral_kernel.py:45-54
+ *   (EigenbasisSumKernel.forward), spectral_kernel.py:96-109 (RandomPhaseKernel.make_embedding, FEAT_* kinds) and the
+ *   lazy Gram spectral_kernel.py:125-127,195-197 (LINEAR kind).
+ * A: [n_rows] x kg_total, B: [n_cols] x kg_total panel-major operands; out: device, layout per epi->out_layout. */
+int lsk_pairwise_poly(const void* A, const void* B, long long n_rows, long long n_cols, int kg_total,
+                      const LskEpilogue* epi, void* out, long long ld_out, void* stream);
+
+/* Lift of n x m frames to SO(n): complete Householder QR (LAPACK conventions) + the sign logic of
+ * Stiefel.M_to_G (reference spaces/stiefel.py:38-48, spaces/grassmannian.py:74-85,120-130).
+ * x: [num, n, m]; out: [num, n, n]; bad_count: device int32, incremented for frames the lift does not reproduce
+ * (the reference's assert, stiefel.py:47). */
+int lsk_lift_frames(const void* x, long long num, int n, int m, void* out, void* bad_count, void* stream);
+
+/* Homogeneous-space pair kernel: for all (i, j), mean over subgroup samples h_k of the class polynomials at
+ * lift(x_i)^T lift(y_j) h_k^T.  Replaces CompactHomogeneousSpace.pairwise_diff/pairwise_embed and
+ * AveragedLieGroupCharacter.forward (reference space.py:125-135, 273-275).  n in {3, 5}.
+ * lifted_x: [n_rows, n, n], lifted_y: [n_cols, n, n], h_samples: [n_avg, n, n]; epi kind FEAT_CHEB1 (n = 3) or
+ * FEAT_SPARSE (n = 5) with one row per output (irrep, or a single collapsed polynomial). */
+int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const void* h_samples, long long n_rows, long long n_cols,
+                    int n, int n_avg, const LskEpilogue* epi, void* out, long long ld_out, void* stream);
+
+/* Spherical-function features on hyperbolic space (ball model):
+ *   F[i,k] = scale * coef[k] * ((1-|x_i|^2)/|x_i - shift_k|^2)^(-i lmd_k + (n-1)/2)
+ * (reference spaces/hyperbolic.py:118-129, 153-158).  x: [n_points, n], shift: [m, n], lmd, coef: [m].
+ * layout ROW_MAJOR / PANEL_MAJOR write the real operand [Re F | Im F] (2m columns); FEAT_COMPLEX writes complex128. */
+int lsk_hyp_features(const void* x, const void* shift, const void* lmd, const void* coef, long long n_points, int m, int n,
+                     double scale, void* out, int layout, long long ld_out, int out_kg, void* stream);
+
+/* Spherical-function features on SPD(n), n = 2..6:
+ *   F[i,k] = scale * coef[k] * exp(sum_r (i lmd[k,r] + rho_r) log a_r(U_i Hinv_k)),  a = |diag R| (Householder QR)
+ * (reference space.py:338-346, 370-380, spaces/spd.py:83-106, 125-129).  chol_upper: [n_points, n, n] = to_group(x),
+ * shift_inv: [m, n, n] = inv(shift), lmd: [m, n], coef: [m]. */
+int lsk_spd_features(const void* chol_upper, const void* shift_inv, const void* lmd, const void* coef, long long n_points,
+                     int m, int n, double scale, void* out, int layout, long long ld_out, int out_kg, void* stream);
+
+/* Batched small-matrix prologues for SPD(n): mode 0 = upper Cholesky factor (reference spaces/spd.py:45-46),
+ * mode 1 = inverse (spaces/spd.py:66-67).  x, out: [num, n, n]; bad_count: device int32 (not PD / singular). */
+int lsk_small_matrix(const void* x, long long num, int n, int mode, void* out, void* bad_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSK_H */

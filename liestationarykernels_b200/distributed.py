@@ -1,0 +1,72 @@
+"""Multi-GPU orchestration: one process per GPU (`torch.distributed`, NCCL over NVLink on the box, gloo in the CPU
+tests).  The reference has no distributed code; the path shards in two ways:
+
+* covariance matrices (EigenbasisSumKernel, Gram of feature maps): x rows are split across ranks, y and the
+  coefficient tables are replicated (a few MB), no collective on the data path; the result stays row-sharded.
+* prior samples (RandomPhaseApproximation / RandomFourierApproximation): the sum over phases / spherical-function
+  features is split across ranks; each rank computes a partial f[N] and one all-reduce(sum) of N doubles finishes it.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def row_shard(n: int, world_size: int, rank: int):
+    """[lo, hi) of the rows owned by `rank`: contiguous, balanced to within one row, covers [0, n) exactly."""
+    return rank * n // world_size, (rank + 1) * n // world_size
+
+
+def phase_shard(num_phases: int, num_irreps: int, world_size: int, rank: int):
+    """Phase range [lo, hi) of `rank` and the indices of its entries in the reference's weight vector, whose layout is
+    irrep-major / phase-minor: weights[l * P + p] (prior_approximation.py:61,87)."""
+    lo, hi = row_shard(num_phases, world_size, rank)
+    idx = (torch.arange(num_irreps)[:, None] * num_phases + torch.arange(lo, hi)[None, :]).reshape(-1)
+    return lo, hi, idx
+
+
+def sharded_covariance(kernel, x, y=None, **kw):
+    """Rows [lo, hi) of kernel(x, y) for this rank. Returns (local_block, lo, hi)."""
+    ws, rk = world()
+    lo, hi = row_shard(x.shape[0], ws, rk)
+    if y is None:
+        y = x
+    return kernel(x[lo:hi].contiguous(), y, **kw), lo, hi
+
+
+class PhaseShardedSampler:
+    """Wraps a RandomPhaseApproximation: every rank keeps a slice of the phases and the matching weights, evaluates the
+    partial sample with the fused feature kernels and all-reduces the [N] vector."""
+
+    def __init__(self, sampler):
+        ws, rk = world()
+        self.full = sampler
+        P, L = sampler.phase_order, sampler.approx_order
+        lo, hi, idx = phase_shard(P, L, ws, rk)
+        self.lo, self.hi = lo, hi
+        self.weight_index = idx.to(sampler.weights.device)
+        self.world_size = ws
+
+    def __call__(self, x):
+        s = self.full
+        import copy
+        local = copy.copy(s)
+        local.phases = s.phases[self.lo:self.hi].contiguous()
+        local.weights = s.weights[self.weight_index].contiguous()
+        local.phase_order = self.hi - self.lo
+        # the 1/sqrt(P) normalisation of the feature map refers to the global number of phases
+        part = local(x) * ((self.hi - self.lo) / s.phase_order) ** 0.5 if self.hi > self.lo else torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)
+        if self.world_size > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        return part
+
+
+def feature_shard(num_features: int, world_size: int, rank: int):
+    """Slice of the spherical-function features owned by `rank` (RandomFourierApproximation sharding)."""
+    return row_shard(num_features, world_size, rank)
