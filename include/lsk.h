@@ -56,7 +56,8 @@ typedef struct LskEpilogue {
     int32_t out_layout;
     int32_t out_kg;                      /* PANEL_MAJOR: k-groups (4 columns) per output row */
     int32_t feat_stride;                 /* FEAT_*: column offset between irreps (= number of phases) */
-    int32_t reserved;                    /* lsk_homog_pairs: bit 0 = pair (y_j, x_i) instead of (x_i, y_j) */
+    int32_t reserved;                    /* bit 0 (lsk_homog_pairs): pair (y_j, x_i) instead of (x_i, y_j);
+                                            bits 8+f (lsk_pairwise_poly): form f enters the affine map squared */
     double scale;
     double aff[LSK_MAX_VARS][1 + LSK_MAX_FORMS];
     double coef[LSK_MAX_COEF];
@@ -71,7 +72,9 @@ long long lsk_embed_buffer_doubles(long long num, int kg_total);
  * Replaces operand preparation of CompactLieGroup.pairwise_diff: inv + cartesian_prod + bmm (reference space.py:62-78,
  * utils.py:40-52, spaces/so.py:124-127, spaces/su.py:79-82).
  * x: [num, n, n] float64 (is_complex = 0) or complex128 (is_complex = 1).  wedge/part/group_begin: host int[nseg].
- * part: 0 real; 1 complex (re,im); 2 complex (re,im) [second operand, real form]; 3 complex (-im,re) [imaginary form]. */
+ * part: 0 real; 1 complex (re,im); 2 complex (re,im) [second operand, real form]; 3 complex (-im,re) [imaginary form].
+ * wedge = 100 (n = 5, real): the 16 rotor coefficients of the Spin(5) lift of x; <R(x), R(y)> = +-cos(t1/2)cos(t2/2)
+ * replaces the 100-term Lambda^2 form for SO(5). */
 int lsk_embed_points(const void* x, long long num, int n, int is_complex, int nseg, const int* wedge, const int* part,
                      const int* group_begin, int kg_total, void* out, void* stream);
 

@@ -22,6 +22,9 @@ from ._lib import (EPI_CHEB1, EPI_ORBIT2, EPI_SPARSE, EPI_STAIR2, MAX_COEF, MAX_
                    LskEpilogue)
 
 
+SPIN5 = 100     # embedding segment code: the 16 rotor coefficients of the Spin(5) lift (csrc/lsk_embed.cu)
+
+
 def _binom(n, k):
     return math.comb(n, k)
 
@@ -29,8 +32,10 @@ def _binom(n, k):
 class GroupPlan:
     """Embedding layout + polynomial tables for one (family, n, order)."""
 
-    def __init__(self, family: str, n: int, order: int):
+    def __init__(self, family: str, n: int, order: int, use_spin: bool = True):
         self.family, self.n, self.order = family, n, order
+        self.use_spin = use_spin
+        self.square_mask = 0
         kept, dropped = ch.truncated_irreps(family, n, order) if order else ([], [])
         self.irreps = kept
         self.dropped = dropped
@@ -51,9 +56,15 @@ class GroupPlan:
             rank = n // 2
             if rank > 3:
                 raise NotImplementedError("SO(%d): compound matrices beyond Lambda^3 are not implemented" % n)
-            for k in range(1, rank + 1):
-                segs_a.append((k, 0))
-                segs_b.append((k, 0))
+            if n == 5 and self.use_spin:
+                # Spin(5) lift: tr g (25-term dot) + the rotor inner product <R_x, R_y> = cos(t1/2) cos(t2/2)
+                # (16-term dot) replace the 100-term Lambda^2 form: K = 44 instead of 128
+                segs_a += [(1, 0), (SPIN5, 0)]
+                segs_b += [(1, 0), (SPIN5, 0)]
+            else:
+                for k in range(1, rank + 1):
+                    segs_a.append((k, 0))
+                    segs_b.append((k, 0))
             self.real_vars = rank
         else:
             if n > 5:
@@ -73,7 +84,7 @@ class GroupPlan:
         begin, g = [], 0
         for (k, part) in segs_a:
             begin.append(g)
-            length = _binom(n, k) ** 2 * (2 if self.is_complex else 1)
+            length = 16 if k == SPIN5 else _binom(n, k) ** 2 * (2 if self.is_complex else 1)
             g += (length + 3) // 4
         self.group_begin = begin
         self.kg_total = g
@@ -102,6 +113,11 @@ class GroupPlan:
             self.M = np.array(mat, dtype=np.float64)
             assert np.all(np.abs(self.M) < 2.0 ** 53)
             self.aff = _so_odd_affine(n)
+            if n == 5 and self.use_spin:
+                # forms: u0 = tr g, u1 = <R_x, R_y> (sign-ambiguous, enters squared):
+                #   s1 = (u0 - 1) / 2,   s2 = (4 u1)^2 / 4 - 1 - s1 = -1/2 - u0 / 2 + 4 u1^2
+                self.aff = [[-0.5, 0.5, 0.0], [-0.5, -0.5, 4.0]]
+                self.square_mask = 0b10
             if rank == 2:
                 self.kind = "rank2"
                 self._build_stair(monos)
@@ -133,7 +149,9 @@ class GroupPlan:
         for (a, b) in monos:
             rows[b] = max(rows.get(b, -1), a)
         nrows = max(rows) + 1
-        self.stair_rows = [rows.get(b, 0) + 1 for b in range(nrows)]
+        # every row is padded to an even number (>= 2) of coefficients with zeros at the high-degree end: the kernel
+        # consumes coefficients two at a time (csrc/lsk_pairwise.cu: epi_stair2)
+        self.stair_rows = [max(2, (rows.get(b, 0) + 2) // 2 * 2) for b in range(nrows)]
         # evaluation order: highest b first, inside a row highest a first
         index = {m: i for i, m in enumerate(monos)}
         order = []
@@ -167,6 +185,7 @@ class GroupPlan:
             ep.group_begin[f] = self.group_begin[f]
             ep.group_end[f] = self.group_end[f]
         ep.nvars = len(self.aff)
+        ep.reserved = self.square_mask << 8
         for v, row in enumerate(self.aff):
             for i, val in enumerate(row):
                 ep.aff[v][i] = float(val)
@@ -446,5 +465,5 @@ def _su_real_character_matrix(n: int, sigs):
 
 
 @lru_cache(maxsize=None)
-def group_plan(family: str, n: int, order: int) -> GroupPlan:
-    return GroupPlan(family, n, order)
+def group_plan(family: str, n: int, order: int, use_spin: bool = True) -> GroupPlan:
+    return GroupPlan(family, n, order, use_spin)

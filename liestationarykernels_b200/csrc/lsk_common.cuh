@@ -17,7 +17,7 @@ constexpr int BM = 128;         // rows per CTA tile  (two A panels)
 constexpr int BN = 64;          // columns per CTA tile (one B panel)
 constexpr int ROW_PAD = 128;    // embedded operands are zero-padded to a multiple of this many rows
 constexpr int KG_PER_STAGE = 8; // k-groups (of 4 doubles) per pipeline stage -> 16 KB per panel per stage
-constexpr int STAGES = 3;       // 3 x (2 A panels + 1 B panel) x 16 KB = 144 KB
+constexpr int STAGES = 4;       // 4 x (2 A panels + 1 B panel) x 16 KB = 192 KB: a whole K=128 tile is prefetched
 constexpr int CONSUMER_WARPS = 16;
 constexpr int THREADS = CONSUMER_WARPS * 32;         // the TMA producer is lane 0 of warp 0
 
@@ -68,6 +68,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// shared-memory loads through an explicit 32-bit shared-window address (computed once per kernel): keeps the
+// generic->shared conversion (an S2UR of the CTA id on sm_100a) out of inner loops
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
 __device__ __forceinline__ void st_cs_f64x2(double* p, double a, double b) {

@@ -8,6 +8,8 @@
 // It replaces the reference's `inv` + `cartesian_prod` + `bmm` operand preparation (space.py:62-78).
 #include "lsk_common.cuh"
 
+#define LSK_SEG_SPIN5 100     // segment code: rotor coefficients of the Spin(5) lift (n = 5, real)
+
 namespace lsk {
 
 struct EmbedSpec {
@@ -74,6 +76,52 @@ __device__ void minor(const double* x, int n, int k, const int (&I)[3], const in
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Spin(5) lift: the rotor R(x) in the even Clifford algebra Cl+(5) (16 real coefficients, index = blade mask >> 1)
+// with R e_a R~ = sum_b x_ba e_b.  x is reduced to the identity by ten Givens rotations, x = G_1^T ... G_10^T, and the
+// rotor is the product of the plane rotors cos(phi/2) - sin(phi/2) e_j e_i.  For g = x y^T:
+//     < R(x), R(y) > = +- cos(theta_1 / 2) cos(theta_2 / 2)
+// (the character of the 4-dimensional spin representation / 4), which together with tr g determines the class of g.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double blade_sign(int a, int b) {
+    int s = 0;
+    a >>= 1;
+    while (a) { s += __popc(a & b); a >>= 1; }
+    return (s & 1) ? -1.0 : 1.0;
+}
+
+__device__ void spin5_rotor(const double* __restrict__ x, double (&R)[16]) {
+    double m[5][5];
+    for (int r = 0; r < 5; ++r)
+        for (int c = 0; c < 5; ++c) m[r][c] = x[r * 5 + c];
+    for (int k = 0; k < 16; ++k) R[k] = 0.0;
+    R[0] = 1.0;
+    for (int j = 0; j < 4; ++j) {
+        for (int i = j + 1; i < 5; ++i) {
+            const double a = m[j][j], b = m[i][j];
+            const double r = hypot(a, b);
+            if (r == 0.0) continue;
+            const double c = a / r, s = b / r;
+            for (int k = 0; k < 5; ++k) {
+                const double rj = m[j][k], ri = m[i][k];
+                m[j][k] = c * rj + s * ri;
+                m[i][k] = -s * rj + c * ri;
+            }
+            double ch, sh;                       // half-angle, formed without cancellation
+            if (c >= 0.0) { ch = sqrt(0.5 * (1.0 + c)); sh = s / (2.0 * ch); }
+            else { sh = (s >= 0.0 ? 1.0 : -1.0) * sqrt(0.5 * (1.0 - c)); ch = s / (2.0 * sh); }
+            const int B = (1 << j) | (1 << i);
+            double nw[16];
+            for (int k = 0; k < 16; ++k) nw[k] = ch * R[k];
+            for (int k = 0; k < 16; ++k) {
+                const int A = (k << 1) | (__popc(k) & 1);          // even-parity 5-bit mask with A >> 1 == k
+                nw[(A ^ B) >> 1] += -sh * blade_sign(A, B) * R[k];
+            }
+            for (int k = 0; k < 16; ++k) R[k] = nw[k];
+        }
+    }
+}
+
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
 embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, EmbedSpec spec, double* __restrict__ out) {
@@ -89,7 +137,9 @@ embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, E
             int seg = 0;
             for (int s = 1; s < spec.nseg; ++s) if (g >= spec.group_begin[s]) seg = s;
             const int e = (g - spec.group_begin[seg]) * 4 + j;
-            if (e < spec.length[seg]) {
+            if (!CPLX && spec.wedge[seg] == LSK_SEG_SPIN5) {
+                continue;                 // written by spin5_embed_kernel (one thread per point)
+            } else if (e < spec.length[seg]) {
                 const int k = spec.wedge[seg], part = spec.part[seg];
                 const int C = binom(n, k);
                 const int el = CPLX ? (e >> 1) : e;
@@ -107,6 +157,24 @@ embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, E
     }
 }
 
+// one thread per point: rotor of the Spin(5) lift into k-groups [g0, g0 + 4) of the panel-major buffer
+__global__ void __launch_bounds__(128)
+spin5_embed_kernel(const double* __restrict__ x, long long num, int kg_total, int g0, double* __restrict__ out) {
+    const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_padded) return;
+    double R[16];
+    if (row < num) spin5_rotor(x + row * 25, R);
+    else for (int k = 0; k < 16; ++k) R[k] = 0.0;
+    double* base = out + ((row >> 6) * kg_total + g0) * (PANEL * 4) + (row & 63) * 4;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        double2* dst = reinterpret_cast<double2*>(base + (size_t)g * (PANEL * 4));
+        dst[0] = make_double2(R[4 * g], R[4 * g + 1]);
+        dst[1] = make_double2(R[4 * g + 2], R[4 * g + 3]);
+    }
+}
+
 }  // namespace lsk
 
 extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_complex, int nseg,
@@ -120,6 +188,13 @@ extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_comp
     spec.nseg = nseg;
     for (int s = 0; s < 4; ++s) { spec.wedge[s] = 1; spec.part[s] = 0; spec.group_begin[s] = 0; spec.length[s] = 0; }
     for (int s = 0; s < nseg; ++s) {
+        if (wedge[s] == LSK_SEG_SPIN5) {
+            if (is_complex || n != 5 || part[s] != 0) return LSK_EARG;
+            spec.wedge[s] = wedge[s]; spec.part[s] = 0; spec.group_begin[s] = group_begin[s]; spec.length[s] = 16;
+            if (group_begin[s] < 0 || group_begin[s] + 4 > kg_total) return LSK_ESIZE;
+            if (s > 0 && group_begin[s] < spec.group_begin[s - 1] + (spec.length[s - 1] + 3) / 4) return LSK_EARG;
+            continue;
+        }
         if (wedge[s] < 1 || wedge[s] > 3 || wedge[s] > n) return LSK_EARG;
         if (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0)) return LSK_EARG;
         int c = 1;
@@ -136,6 +211,13 @@ extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_comp
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (is_complex) embed_kernel<true><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
     else embed_kernel<false><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
+    for (int s = 0; s < nseg; ++s) {
+        if (spec.wedge[s] == LSK_SEG_SPIN5) {
+            const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
+            spin5_embed_kernel<<<(unsigned)((rows_padded + 127) / 128), 128, 0, st>>>(
+                static_cast<const double*>(x), num, kg_total, spec.group_begin[s], static_cast<double*>(out));
+        }
+    }
     return (int)cudaGetLastError();
 }
 

@@ -56,7 +56,9 @@ class CompactHomogeneousSpace(AbstractManifold):
         self.order, self.average_order = self.g.order, average_order
         self.h_samples = self.sample_H(self.average_order)
         self.lb_eigenspaces = [AveragedLBEigenspace(rep, self) for rep in self.g.lb_eigenspaces]
-        self.plan = self.g.plan
+        # the pair kernel forms tr g and e_2(g) itself: same polynomials, classical (non-spinor) variable map
+        from ..classfn import group_plan
+        self.plan = group_plan("SO", self.g.n, self.g.order, False)
 
     @property
     def _lambdas(self):

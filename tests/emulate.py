@@ -19,10 +19,54 @@ def compound(x, k):
     return out
 
 
+_EVEN = [m for m in range(32) if bin(m).count("1") % 2 == 0]
+
+
+def _blade_sign(a, b):
+    s = 0
+    a >>= 1
+    while a:
+        s += bin(a & b).count("1")
+        a >>= 1
+    return -1.0 if s & 1 else 1.0
+
+
+def spin5_rotor(x):
+    """16 rotor coefficients (index = even blade mask >> 1) of the Spin(5) lift, by Givens elimination."""
+    m = np.array(x, dtype=np.float64)
+    R = np.zeros(16)
+    R[0] = 1.0
+    for j in range(4):
+        for i in range(j + 1, 5):
+            a, b = m[j, j], m[i, j]
+            r = np.hypot(a, b)
+            if r == 0:
+                continue
+            c, s = a / r, b / r
+            rj, ri = m[j].copy(), m[i].copy()
+            m[j], m[i] = c * rj + s * ri, -s * rj + c * ri
+            if c >= 0:
+                ch = np.sqrt((1 + c) / 2)
+                sh = s / (2 * ch)
+            else:
+                sh = (1.0 if s >= 0 else -1.0) * np.sqrt((1 - c) / 2)
+                ch = s / (2 * sh)
+            B = (1 << j) | (1 << i)
+            new = ch * R
+            for idx in range(16):
+                A = _EVEN[idx]
+                new[(A ^ B) >> 1] += -sh * _blade_sign(A, B) * R[idx]
+            R = new
+    return R
+
+
 def embed(plan, x, side):
     segs = plan.segments_a if side == "a" else plan.segments_b
     cols = []
     for (k, part) in segs:
+        if k == 100:
+            cols.append(np.stack([spin5_rotor(xi) for xi in x]))
+            continue
         c = compound(x, k).reshape(x.shape[0], -1)
         if part == 0:
             v = c.real
@@ -38,7 +82,9 @@ def embed(plan, x, side):
 
 def run_epilogue(ep, forms):
     """forms: [nforms, N, M] -> [N, M]"""
-    var = [ep.aff[v][0] + sum(ep.aff[v][1 + f] * forms[f] for f in range(ep.nforms)) for v in range(ep.nvars)]
+    sq = (ep.reserved >> 8) & 0xF
+    w = [forms[f] * forms[f] if (sq >> f) & 1 else forms[f] for f in range(ep.nforms)]
+    var = [ep.aff[v][0] + sum(ep.aff[v][1 + f] * w[f] for f in range(ep.nforms)) for v in range(ep.nvars)]
     coef = np.array(ep.coef[:])
     if ep.kind == _lib.EPI_CHEB1:
         x = var[0]
