@@ -59,6 +59,8 @@ typedef struct LskEpilogue {
     int32_t reserved;                    /* bit 0 (lsk_homog_pairs): pair (y_j, x_i) instead of (x_i, y_j);
                                             bits 8+f (lsk_pairwise_poly): form f enters the affine map squared */
     double scale;
+    unsigned long long stair_shape;      /* STAIR2: coefficient pairs of row slot k (evaluation order) in bits [4k, 4k+4);
+                                            row slot k starts at coef[16 k] */
     double aff[LSK_MAX_VARS][1 + LSK_MAX_FORMS];
     double coef[LSK_MAX_COEF];
 } LskEpilogue;

@@ -37,6 +37,7 @@ class LskEpilogue(ctypes.Structure):
         ("feat_stride", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
         ("scale", ctypes.c_double),
+        ("stair_shape", ctypes.c_uint64),
         ("aff", (ctypes.c_double * (1 + MAX_FORMS)) * MAX_VARS),
         ("coef", ctypes.c_double * MAX_COEF),
     ]

@@ -145,21 +145,24 @@ class GroupPlan:
         self.aff = [[0.0] + [1.0 if f == v else 0.0 for f in range(self.nforms)] for v in range(self.nforms)]
 
     def _build_stair(self, monos):
+        """Layout of the fast (monomial) form for csrc/lsk_pairwise.cu `epi_stair2`: row slot k (evaluation order,
+        highest power of s2 first) holds sum_a C[b][a] s1^a, highest a first, padded with zeros at the high end to an
+        even number of coefficients, at the fixed offset 16 k; the pair counts go into a 64-bit shape word."""
         rows = {}
         for (a, b) in monos:
             rows[b] = max(rows.get(b, -1), a)
         nrows = max(rows) + 1
-        # every row is padded to an even number (>= 2) of coefficients with zeros at the high-degree end: the kernel
-        # consumes coefficients two at a time (csrc/lsk_pairwise.cu: epi_stair2)
         self.stair_rows = [max(2, (rows.get(b, 0) + 2) // 2 * 2) for b in range(nrows)]
-        # evaluation order: highest b first, inside a row highest a first
+        self.stair_ok = nrows <= 16 and max(self.stair_rows) <= 16
         index = {m: i for i, m in enumerate(monos)}
-        order = []
-        for b in range(nrows - 1, -1, -1):
-            for a in range(self.stair_rows[b] - 1, -1, -1):
-                order.append(index.get((a, b), -1))
-        self.stair_order = np.array(order)
-        self.stair_ok = nrows <= MAX_ROWS and len(order) <= MAX_COEF
+        self.stair_slots = []            # (offset in coef[], monomial index or -1)
+        self.stair_shape = 0
+        for slot, b in enumerate(range(nrows - 1, -1, -1)):
+            ln = self.stair_rows[b]
+            if self.stair_ok:
+                self.stair_shape |= (ln // 2) << (4 * slot)
+            for pos, a in enumerate(range(ln - 1, -1, -1)):
+                self.stair_slots.append((16 * slot + pos, index.get((a, b), -1)))
 
     def _build_orbit(self, sigs):
         # W[mu] = sum_l w_l m_l(mu);  full symmetric Chebyshev-product matrix (see lsk_pairwise.cu epi_orbit2)
@@ -212,10 +215,11 @@ class GroupPlan:
                     raise ValueError("staircase table too large for the fast form")
                 coef = _dot_long(w, self.M)
                 ep.kind, ep.nterms = EPI_STAIR2, len(self.stair_rows)
-                for b, ln in enumerate(self.stair_rows):
-                    ep.row_len[b] = ln
-                for i, j in enumerate(self.stair_order):
-                    ep.coef[i] = coef[j] if j >= 0 else 0.0
+                ep.stair_shape = self.stair_shape
+                for slot, ln in enumerate(reversed(self.stair_rows)):
+                    ep.row_len[slot] = ln
+                for off, j in self.stair_slots:
+                    ep.coef[off] = coef[j] if j >= 0 else 0.0
                 return ep
             D = self.orbit_D
             if D > 20:
@@ -347,14 +351,11 @@ class GroupPlan:
         robust = (_dot_long(w, self.M_orbit) * self.orbit_fac) @ orb
         coef = _dot_long(w, self.M)
         fast = np.zeros_like(s1)
-        pos = 0
-        table = [coef[j] if j >= 0 else 0.0 for j in self.stair_order]
-        for b in range(len(self.stair_rows) - 1, -1, -1):
-            ln = self.stair_rows[b]
-            inner = np.full_like(s1, table[pos])
+        table = {off: (coef[j] if j >= 0 else 0.0) for off, j in self.stair_slots}
+        for slot, ln in enumerate(reversed(self.stair_rows)):
+            inner = np.full_like(s1, table[16 * slot])
             for a in range(1, ln):
-                inner = inner * s1 + table[pos + a]
-            pos += ln
+                inner = inner * s1 + table[16 * slot + a]
             fast = fast * s2 + inner
         denom = np.maximum(np.abs(robust), 1e-300)
         return bool(np.max(np.abs(fast - robust) / denom) < tol)

@@ -50,36 +50,38 @@ __device__ __forceinline__ void epi_cheb1(const double* coef, int nterms, const 
 
 template <int R>
 __device__ __forceinline__ void epi_stair2(const LskEpilogue& p, const double (&s1)[R], const double (&s2)[R], double (&out)[R]) {
-    // sum_b s2^b ( sum_a C[b][a] s1^a ) by nested Horner; coefficients in evaluation order (highest b first, highest
-    // a first), every row padded by the host to an even length >= 2.  All loop counters and coefficient indices are
-    // warp-uniform and the coefficients sit in the kernel-parameter constant bank, so the compiler keeps the whole
-    // control flow and the coefficient fetch on the uniform datapath (LDCU -> DFMA with a uniform-register operand):
-    // measured 93 % of the DFMA peak for this loop shape against 73-84 % for shared-memory coefficients or a per-step
-    // branch (tools/horner_loop.cu, profiles/horner_loop_r01.json).
+    // sum_b s2^b ( sum_a C[b][a] s1^a ) by nested Horner.  Row slot k (evaluation order) sits at the fixed offset 16 k
+    // of coef[], holds 2 * pairs_k coefficients (highest power first, zero-padded to even length) and pairs_k comes
+    // from 4 bits of the uniform shape word.  The row loop is unrolled, so the code is a sequence of simple
+    // runtime-trip-count loops whose bounds and coefficient addresses are warp-uniform: ptxas keeps all of it on the
+    // uniform datapath (LDCU + DFMA with a uniform-register operand, UISETP/BRA.U loop control).  Nested
+    // data-dependent loops, a per-step branch or shared-memory coefficients each cost 10-25 % of the DFMA rate
+    // (tools/horner_loop.cu, profiles/horner_loop_r01.json).
     double outer[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) outer[r] = 0.0;
-    int pos = 0;
-    const int rows = p.nterms;
-    for (int b = rows - 1; b >= 0; --b) {
-        const int pairs = p.row_len[b] >> 1;
-        double inner[R];
-        {
-            const double c0 = p.coef[pos], c1 = p.coef[pos + 1];
+    const unsigned long long shape = p.stair_shape;
 #pragma unroll
-            for (int r = 0; r < R; ++r) inner[r] = fma(s1[r], c0, c1);
-        }
+    for (int k = 0; k < LSK_STAIR_MAX_ROWS; ++k) {
+        const int pairs = (int)((shape >> (4 * k)) & 15ull);
+        if (pairs > 0) {
+            double inner[R];
+            {
+                const double c0 = p.coef[LSK_STAIR_STRIDE * k], c1 = p.coef[LSK_STAIR_STRIDE * k + 1];
+#pragma unroll
+                for (int r = 0; r < R; ++r) inner[r] = fma(s1[r], c0, c1);
+            }
 #pragma unroll 2
-        for (int a = 1; a < pairs; ++a) {
-            const double c0 = p.coef[pos + 2 * a], c1 = p.coef[pos + 2 * a + 1];
+            for (int q = 1; q < pairs; ++q) {
+                const double c0 = p.coef[LSK_STAIR_STRIDE * k + 2 * q], c1 = p.coef[LSK_STAIR_STRIDE * k + 2 * q + 1];
 #pragma unroll
-            for (int r = 0; r < R; ++r) inner[r] = fma(inner[r], s1[r], c0);
+                for (int r = 0; r < R; ++r) inner[r] = fma(inner[r], s1[r], c0);
 #pragma unroll
-            for (int r = 0; r < R; ++r) inner[r] = fma(inner[r], s1[r], c1);
+                for (int r = 0; r < R; ++r) inner[r] = fma(inner[r], s1[r], c1);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) outer[r] = fma(outer[r], s2[r], inner[r]);
         }
-        pos += 2 * pairs;
-#pragma unroll
-        for (int r = 0; r < R; ++r) outer[r] = fma(outer[r], s2[r], inner[r]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) out[r] = outer[r];
@@ -188,10 +190,15 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     int p_form = 0, p_group = p.group_begin[0], p_stage = 0;
     uint32_t p_phase = 0;
     int issued_ahead = 0;                       // chunks issued but not yet consumed by warp 0
-    auto produce = [&](bool blocking) -> bool {
-        if (p_tile >= n_tiles) return false;
-        if (blocking) mbar_wait(&empty_bar[p_stage], p_phase ^ 1);      // first pass over the ring returns immediately
-        else if (!mbar_test(&empty_bar[p_stage], p_phase ^ 1)) return false;
+    // One non-blocking attempt to issue the next chunk.  LOOP-FREE on purpose: a loop (even an inline-asm spin) under a
+    // thread-divergent branch makes ptxas give up warp-uniformity for the whole enclosing tile loop, which moves the
+    // epilogue's coefficient fetch from the uniform datapath (LDCU + uniform-register operands) to per-thread LDC and
+    // costs ~15 % of its DFMA rate.  `wait_hw` = use the hardware-suspending try_wait instead of a plain test.
+    auto produce_once = [&](bool wait_hw) -> bool {
+        if (p_tile >= n_tiles) return true;                           // nothing left: treat as done
+        const bool free_slot = wait_hw ? mbar_try_wait_once(&empty_bar[p_stage], p_phase ^ 1)
+                                       : mbar_test(&empty_bar[p_stage], p_phase ^ 1);   // first ring pass: immediately true
+        if (!free_slot) return false;
         const int pr = (int)(p_tile / col_panels), pc = (int)(p_tile % col_panels);
         const double* srcA0 = A + ((size_t)(2 * pr) * kg_total + p_group) * (PANEL * 4);   // operands are padded to
         const double* srcA1 = srcA0 + (size_t)kg_total * (PANEL * 4);                       // ROW_PAD rows: both exist
@@ -211,10 +218,26 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         ++issued_ahead;
         return true;
     };
-    // keep the ring full without ever blocking (called by warp 0 wherever it is cheap)
+    // keep the ring full without ever blocking (thread 0; called wherever it is cheap)
     auto produce_ahead = [&]() {
         if (threadIdx.x == 0) {
-            while (issued_ahead < STAGES) if (!produce(false)) break;
+#pragma unroll
+            for (int k = 0; k < STAGES; ++k)
+                if (issued_ahead < STAGES) produce_once(false);
+        }
+    };
+    // the chunk a warp is about to wait for must be in flight: warp-uniform poll loop (the vote makes the trip count
+    // uniform; only thread 0 of the CTA ever polls, every other warp leaves after one iteration)
+    auto produce_blocking = [&]() {
+        bool need = (threadIdx.x == 0) && (issued_ahead == 0);
+        unsigned done = 0;
+        while (!done) {
+            unsigned ok = 1;
+            if (need) {
+                ok = produce_once(true) ? 1u : 0u;
+                if (ok) need = false;
+            }
+            done = __all_sync(0xffffffffu, ok);
         }
     };
 
@@ -244,11 +267,8 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             const int g_end = p.group_end[f];
             for (int g = p.group_begin[f], ng; g < g_end; g += ng) {
                 ng = chunk_len(g_end - g);
-                if (threadIdx.x == 0) {
-                    if (issued_ahead == 0) produce(true);      // the chunk we are about to wait for must be in flight
-                    while (issued_ahead < STAGES) if (!produce(false)) break;
-                }
-                __syncwarp();
+                produce_ahead();
+                produce_blocking();
                 mbar_wait(&full_bar[stage], phase);
                 const double* pa = sA + stage * A_STAGE + a_off;
                 const double* pb = sB + stage * B_STAGE + b_off;
@@ -323,17 +343,19 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             double var[NV][R], res[R];
 #pragma unroll
             for (int e = 0; e < R; ++e) {
-                const int m = 2 * h + (e >> 2), n = (e >> 1) & 1, i = e & 1;
+                const int ml = e >> 2, n = (e >> 1) & 1, i = e & 1;
+                double u[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) u[f] = acc[f][2 * h + ml][n][i];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    if constexpr (EPI == LSK_EPI_LINEAR) var[v][e] = acc[0][m][n][i];
+                    if constexpr (EPI == LSK_EPI_LINEAR) var[v][e] = u[0];
                     else {
                         // forms flagged in bits 8.. of `reserved` enter squared (sign-ambiguous spinor form)
                         double x = p.aff[v][0];
 #pragma unroll
                         for (int f = 0; f < NF; ++f) {
-                            const double u = acc[f][m][n][i];
-                            const double w = ((p.reserved >> (8 + f)) & 1) ? u * u : u;
+                            const double w = ((p.reserved >> (8 + f)) & 1) ? u[f] * u[f] : u[f];
                             x = fma(p.aff[v][1 + f], w, x);
                         }
                         var[v][e] = x;
@@ -434,10 +456,11 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.nforms == 1) LSK_GO(LSK_EPI_CHEB1, 1, 1, 1);
         return LSK_EUNSUPPORTED;
     case LSK_EPI_STAIR2: {
-        if (p.nterms < 1 || p.nterms > LSK_MAX_ROWS || p.nvars != 2) return LSK_EARG;
-        int tot = 0;
-        for (int b2 = 0; b2 < p.nterms; ++b2) { if (p.row_len[b2] < 2 || (p.row_len[b2] & 1)) return LSK_EARG; tot += p.row_len[b2]; }
-        if (tot > LSK_MAX_COEF) return LSK_ESIZE;
+        if (p.nterms < 1 || p.nterms > LSK_STAIR_MAX_ROWS || p.nvars != 2) return LSK_EARG;
+        for (int k = 0; k < LSK_STAIR_MAX_ROWS; ++k) {
+            const int pairs = (int)((p.stair_shape >> (4 * k)) & 15ull);
+            if (k < p.nterms ? (pairs < 1 || 2 * pairs > LSK_STAIR_STRIDE || p.row_len[k] != 2 * pairs) : pairs != 0) return LSK_EARG;
+        }
         if (p.nforms == 2) LSK_GO(LSK_EPI_STAIR2, 2, 2, 1);
         return LSK_EUNSUPPORTED;
     }

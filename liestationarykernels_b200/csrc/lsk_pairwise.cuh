@@ -6,6 +6,8 @@
 #define LSK_MAX_VARS 4
 #define LSK_MAX_COEF 400
 #define LSK_MAX_ROWS 24
+#define LSK_STAIR_MAX_ROWS 16    // STAIR2: rows sit at a fixed stride of LSK_STAIR_STRIDE coefficients
+#define LSK_STAIR_STRIDE 16
 
 // Epilogue kinds: how the class function is evaluated from the conjugation invariants.
 #define LSK_EPI_CHEB1   1   // rank 1:  sum_k coef[k] T_k(var0)                          (Clenshaw; SO(3), SU(2))
@@ -36,6 +38,7 @@ struct LskEpilogue {
     int32_t feat_stride;                   // FEAT_*: column offset between consecutive irreps (= number of phases)
     int32_t reserved;
     double scale;
+    unsigned long long stair_shape;        // STAIR2: coefficient pairs of row slot k (evaluation order) in bits [4k, 4k+4)
     double aff[LSK_MAX_VARS][1 + LSK_MAX_FORMS];
     double coef[LSK_MAX_COEF];
 };

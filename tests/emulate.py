@@ -96,13 +96,12 @@ def run_epilogue(ep, forms):
     elif ep.kind == _lib.EPI_STAIR2:
         s1, s2 = var
         res = np.zeros_like(s1)
-        pos = 0
-        for b in range(ep.nterms - 1, -1, -1):
-            ln = ep.row_len[b]
-            inner = np.full_like(s1, coef[pos])
+        for slot in range(ep.nterms):
+            ln = 2 * ((ep.stair_shape >> (4 * slot)) & 15)
+            assert ln == ep.row_len[slot]
+            inner = np.full_like(s1, coef[16 * slot])
             for a in range(1, ln):
-                inner = inner * s1 + coef[pos + a]
-            pos += ln
+                inner = inner * s1 + coef[16 * slot + a]
             res = res * s2 + inner
     elif ep.kind == _lib.EPI_ORBIT2:
         s1, s2 = var

@@ -29,9 +29,9 @@ def test_library_exports_every_declared_symbol():
 def test_epilogue_struct_layout_matches_header():
     from liestationarykernels_b200 import _lib
     # C layout: 4 + 4 + 4 + 24 + 4 int32 = 40 ints = 160 bytes, then 1 + 4*5 + 400 doubles
-    assert ctypes.sizeof(_lib.LskEpilogue) == 160 + 8 * (1 + 20 + 400)
+    assert ctypes.sizeof(_lib.LskEpilogue) == 160 + 8 * (2 + 20 + 400)
     assert _lib.LskEpilogue.scale.offset == 160
-    assert _lib.LskEpilogue.coef.offset == 160 + 8 * 21
+    assert _lib.LskEpilogue.coef.offset == 160 + 8 * 22
     assert ctypes.sizeof(_lib.LskEpilogue) < 4096, "must fit the kernel-parameter constant bank"
 
 

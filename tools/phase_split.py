@@ -48,13 +48,11 @@ lin2 = _lib.LskEpilogue.from_buffer_copy(bytes(lin))
 lin2.group_end[0] = 2
 res["store_only_ms"] = timeit(lambda: ops.pairwise_poly(small, small, N, N, 2, lin2, out=out))
 print(json.dumps(res))
-ep3 = _lib.LskEpilogue.from_buffer_copy(bytes(ep2))
-ep3.nterms = 1
-ep3.row_len[0] = 2
-res2 = {"epilogue_1row_ms": timeit(lambda: ops.pairwise_poly(small, small, N, N, 2, ep3, out=out))}
-for rows in (3, 6, 11):
+res2 = {}
+for rows in (1, 3, 6, 11):
     e = _lib.LskEpilogue.from_buffer_copy(bytes(ep2))
     e.nterms = rows
+    e.stair_shape = ep2.stair_shape & ((1 << (4 * rows)) - 1)
     steps = sum(e.row_len[i] for i in range(rows)) // 2
     res2["epilogue_%drows_%dsteps_ms" % (rows, steps)] = timeit(lambda: ops.pairwise_poly(small, small, N, N, 2, e, out=out))
 print(json.dumps(res2))
