@@ -90,6 +90,9 @@ def oracle_block(workload, nx, ny, seed=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import lsk_oracle as orc
     w = WORKLOADS[workload]
+    # all host cores (torchrun exports OMP_NUM_THREADS=1, which would handicap the CPU arm)
+    if torch.get_num_threads() < (os.cpu_count() or 1):
+        torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(seed)
     og = orc.Group(w["group"], w["n"], w["order"])
     om = orc.Measure(w["measure"]["kind"], w["measure"]["dim"], w["measure"]["lengthscale"], w["measure"].get("nu"))

@@ -121,6 +121,15 @@ int lsk_spd_features(const void* chol_upper, const void* shift_inv, const void* 
  * mode 1 = inverse (spaces/spd.py:66-67).  x, out: [num, n, n]; bad_count: device int32 (not PD / singular). */
 int lsk_small_matrix(const void* x, long long num, int n, int mode, void* out, void* bad_count, void* stream);
 
+/* Haar samples from Gaussian draws: Householder QR (LAPACK conventions), q *= sign(diag r) (SU: conjugate phase),
+ * q[:, :, 0] *= sign(det q) (SU: conjugate phase of det) - the deterministic part of SO.rand / SU.rand / SPD.rand_phase
+ * (reference spaces/so.py:93-100, spaces/su.py:56-64, spaces/spd.py:48-55).  gauss, out: [num, n, n] float64 or complex128. */
+int lsk_haar_from_gaussian(const void* gauss, long long num, int n, int is_complex, void* out, void* stream);
+
+/* Unit-quaternion parametrisation of SO(3) (to_su2 = 0, reference spaces/so.py:74-92) or SU(2) (to_su2 = 1,
+ * spaces/su.py:47-55).  gauss: [num, 4] float64;  out: [num, 3, 3] float64 or [num, 2, 2] complex128. */
+int lsk_quaternion_to_group(const void* gauss, long long num, int to_su2, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

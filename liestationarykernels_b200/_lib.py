@@ -68,6 +68,9 @@ _PROTOTYPES = {
                                         ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
     "lsk_small_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "lsk_haar_from_gaussian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
+    "lsk_quaternion_to_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "lsk_pairwise_poly": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
                                          ctypes.POINTER(LskEpilogue), ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
 }

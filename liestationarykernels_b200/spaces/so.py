@@ -80,20 +80,25 @@ class SO(CompactLieGroup):
 
 
 def quaternion_to_so3(q):
-    """Unit-quaternion parametrisation used by the reference for SO(3) (so.py:74-92); `q` is the [num,4] Gaussian draw."""
-    q = q / torch.linalg.vector_norm(q, dim=-1, keepdim=True)
-    x, y, z, w = (q[..., i].unsqueeze(-1) for i in range(4))
-    xx, yy, zz = x ** 2, y ** 2, z ** 2
-    xy, xz, xw, yz, yw, zw = x * y, x * z, x * w, y * z, y * w, z * w
-    r1 = torch.hstack((1 - 2 * (yy + zz), 2 * (xy - zw), 2 * (xz + yw))).unsqueeze(-1)
-    r2 = torch.hstack((2 * (xy + zw), 1 - 2 * (xx + zz), 2 * (yz - xw))).unsqueeze(-1)
-    r3 = torch.hstack((2 * (xz - yw), 2 * (yz + xw), 1 - 2 * (xx + yy))).unsqueeze(-1)
-    return torch.cat((r1, r2, r3), -1)
+    """Unit-quaternion parametrisation used by the reference for SO(3) (so.py:74-92); `q` is the [num, 4] Gaussian draw.
+    CUDA kernel `lsk_quaternion_to_group`."""
+    from .. import _lib
+    lib = _lib.load()
+    q = q.to(dtype).contiguous()
+    out = torch.empty((q.shape[0], 3, 3), dtype=dtype, device=q.device)
+    _lib.check(lib.lsk_quaternion_to_group(_lib.ptr(q), q.shape[0], 0, _lib.ptr(out), _lib.stream_ptr()), "lsk_quaternion_to_group")
+    _lib.count_launch()
+    return out
 
 
 def haar_from_gaussian(h):
-    """QR of a Gaussian batch, column signs from diag(R), determinant fixed on column 0 (so.py:94-100)."""
-    q, r = torch.linalg.qr(h)
-    q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1))[:, None]
-    q[:, :, 0] *= torch.sign(torch.det(q))[:, None]
-    return q
+    """QR of a Gaussian batch, column signs from diag(R), determinant fixed on column 0 (so.py:94-100):
+    CUDA kernel `lsk_haar_from_gaussian` (one thread per matrix, LAPACK Householder conventions)."""
+    from .. import _lib
+    lib = _lib.load()
+    h = h.to(dtype).contiguous()
+    out = torch.empty_like(h)
+    _lib.check(lib.lsk_haar_from_gaussian(_lib.ptr(h), h.shape[0], h.shape[-1], 0, _lib.ptr(out), _lib.stream_ptr()),
+               "lsk_haar_from_gaussian")
+    _lib.count_launch()
+    return out

@@ -53,18 +53,24 @@ class SU(CompactLieGroup):
 
 
 def quaternion_to_su2(sp):
-    sp = sp / torch.linalg.vector_norm(sp, dim=-1, keepdim=True)
-    a = torch.view_as_complex(sp[..., :2].contiguous()).unsqueeze(-1)
-    b = torch.view_as_complex(sp[..., 2:].contiguous()).unsqueeze(-1)
-    r1 = torch.hstack((a, -b.conj())).unsqueeze(-1)
-    r2 = torch.hstack((b, a.conj())).unsqueeze(-1)
-    return torch.cat((r1, r2), -1)
+    """su.py:47-55; CUDA kernel `lsk_quaternion_to_group`."""
+    from .. import _lib
+    lib = _lib.load()
+    sp = sp.to(torch.float64).contiguous()
+    out = torch.empty((sp.shape[0], 2, 2), dtype=dtype, device=sp.device)
+    _lib.check(lib.lsk_quaternion_to_group(_lib.ptr(sp), sp.shape[0], 1, _lib.ptr(torch.view_as_real(out)), _lib.stream_ptr()),
+               "lsk_quaternion_to_group")
+    _lib.count_launch()
+    return out
 
 
 def haar_from_gaussian_complex(h):
-    q, r = torch.linalg.qr(h)
-    rd = torch.diagonal(r, dim1=-2, dim2=-1)
-    q = q * torch.conj(rd / torch.abs(rd))[:, None]
-    qd = torch.det(q)
-    q[:, :, 0] *= torch.conj(qd / torch.abs(qd))[:, None]
-    return q
+    """su.py:56-64; CUDA kernel `lsk_haar_from_gaussian` (complex Householder QR, unit-phase fixes)."""
+    from .. import _lib
+    lib = _lib.load()
+    h = h.to(dtype).contiguous()
+    out = torch.empty_like(h)
+    _lib.check(lib.lsk_haar_from_gaussian(_lib.ptr(torch.view_as_real(h)), h.shape[0], h.shape[-1], 1,
+                                          _lib.ptr(torch.view_as_real(out)), _lib.stream_ptr()), "lsk_haar_from_gaussian")
+    _lib.count_launch()
+    return out
