@@ -32,6 +32,46 @@ def spectral_weights(measure, manifold):
     return a.detach().cpu().numpy()
 
 
+class _WeightedCharacterSum(torch.autograd.Function):
+    """K = sum_l c_l(theta) d_l Re chi_l(x_i y_j^{-1}) with hyper-parameter gradients.
+
+    d/dtheta of the covariance is the same class-function sum with the weights dc_l/dtheta, so the backward pass is
+    one more launch of the fused kernel per hyper-parameter followed by <G, K'>: nothing per-irrep of size N*M is ever
+    stored (the reference keeps L such tensors alive in its autograd graph).  dc/dtheta comes from forward-mode AD of
+    the tiny L-vector function theta -> c(theta).  Inputs x, y get no gradient."""
+
+    @staticmethod
+    def forward(ctx, kernel, x, y, normalize, out, *params):
+        ctx.kernel, ctx.normalize = kernel, normalize
+        ctx.x, ctx.y = x, y
+        ctx.n_params = len(params)
+        with torch.no_grad():
+            c = kernel._coefficient_vector(normalize, params)
+        return kernel._evaluate(x, y, c.detach().cpu().numpy(), out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        kernel = ctx.kernel
+        params = kernel._hyper_parameters()
+        grads = []
+        for i in range(ctx.n_params):
+            if not ctx.needs_input_grad[5 + i]:
+                grads.append(None)
+                continue
+
+            def f(p, i=i):
+                ps = list(params)
+                ps[i] = p
+                return kernel._coefficient_vector(ctx.normalize, ps)
+
+            with torch.enable_grad():
+                _, tangent = torch.func.jvp(f, (params[i].detach(),), (torch.ones_like(params[i]),))
+            with torch.no_grad():
+                dk = kernel._evaluate(ctx.x, ctx.y, tangent.detach().cpu().numpy(), None)
+                grads.append((grad * dk).sum().reshape(params[i].shape))
+        return (None, None, None, None, None, *grads)
+
+
 class EigenbasisSumKernel(AbstractSpectralKernel):
     """k(x, y) = |sigma^2| / norm * sum_l a(lambda_l) d_l Re chi_l(x y^{-1})   (spectral_kernel.py:26-54)."""
 
@@ -55,8 +95,40 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         manifold = self.manifold
         if not isinstance(manifold, CompactLieGroup):
             return manifold._eigensum(self, x, y, normalize, out)
+        params = self._hyper_parameters()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _WeightedCharacterSum.apply(self, x, y, normalize, out, *params)
         plan = manifold.plan
         ep = self._epilogue(normalize)
+        ea = ops.embed(plan, x, "a")
+        eb = ea if (y is x and not plan.is_complex) else ops.embed(plan, y, "b")
+        return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out)
+
+    # ---- differentiable path ---------------------------------------------------------------------------------
+    def _hyper_parameters(self):
+        return [self.measure.lengthscale, self.measure.variance]
+
+    def _coefficient_vector(self, normalize, params):
+        """c_l = |sigma^2| a_l(lengthscale) / normaliser as a torch function of the hyper-parameters.  In training mode
+        the normaliser is the kernel at the identity class, sum_l a_l d_l^2, recomputed from the same parameters
+        (spectral_kernel.py:33-35, 41-43); in eval mode it is the stored constant."""
+        ls, var = params
+        m = self.measure
+        lam = self.manifold._lambdas
+        if hasattr(m, "nu"):
+            a = torch.pow(m.nu / (ls * ls / 2.0) + lam, -m.nu - m.dim / 2)
+        else:
+            a = torch.exp(-ls * ls / 2.0 * lam)
+        if not normalize:
+            return a
+        dims = torch.as_tensor(self.manifold._dims, dtype=dtype, device=a.device)
+        norm = (a * dims * dims).sum() if self.training else torch.as_tensor(self.normalizer, dtype=dtype, device=a.device).detach()
+        return torch.abs(var[0]) * a / norm
+
+    def _evaluate(self, x, y, coefs, out):
+        manifold = self.manifold
+        plan = manifold.plan
+        ep = plan.epilogue(np.asarray(coefs, dtype=np.float64) * manifold._dims, 1.0, form=self.form)
         ea = ops.embed(plan, x, "a")
         eb = ea if (y is x and not plan.is_complex) else ops.embed(plan, y, "b")
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out)
