@@ -248,6 +248,14 @@ def run_ours(args):
         except Exception:
             hbm_peak = 6650.0
         store_gbs = (hi - lo) * M * 8 / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        try:    # dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture (same workload, N=1)
+            with open(os.path.join(ROOT, "profiles", "pairwise_traffic_r01.json")) as fh:
+                tj = json.load(fh)
+            if args.workload == "so5" and args.size == 16384 and world == 1:
+                traffic = tj["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
         # cpu baseline: bounded block of the same workload through the oracle port on the host cores (N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -265,7 +273,7 @@ def run_ours(args):
                        "cache": "output (%.2f GB per step) is far larger than L2 and rewritten every step; the 2x%.1f MB inputs are L2-resident by nature" % ((hi - lo) * M * 8 / 1e9, N * w["n"] ** 2 * (16 if w["group"] == "SU" else 8) / 1e6),
                        "polynomial_form": {2: "monomial staircase (fast)", 3: "Weyl-orbit Chebyshev (robust)", 1: "Clenshaw", 4: "sparse"}[ep.kind]},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "lsk::pairwise_kernel", "kernel_ms": kern_ms,
+                         "traffic": traffic, "kernel": "lsk::pairwise_kernel", "kernel_ms": kern_ms,
                          "flop_per_entry_algorithmic": flop, "peak_source": peak_src,
                          "secondary_hbm": {"achieved": store_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": store_gbs / hbm_peak}},
             "e2e": {"value": res[True], "unit": "entries/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size() + yh.numel() * yh.element_size()),
