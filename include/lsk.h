@@ -57,6 +57,8 @@ typedef struct LskEpilogue {
     int32_t out_kg;                      /* PANEL_MAJOR: k-groups (4 columns) per output row */
     int32_t feat_stride;                 /* FEAT_*: column offset between irreps (= number of phases) */
     int32_t reserved;                    /* bit 0 (lsk_homog_pairs): pair (y_j, x_i) instead of (x_i, y_j);
+                                            bit 1 (lsk_pairwise_poly): symmetric problem (A, B describe the same points, square
+                                            row-major output): only the upper triangle of tiles is computed and mirrored;
                                             bits 8+f (lsk_pairwise_poly): form f enters the affine map squared */
     double scale;
     unsigned long long stair_shape;      /* STAIR2: coefficient pairs of row slot k (evaluation order) in bits [4k, 4k+4);

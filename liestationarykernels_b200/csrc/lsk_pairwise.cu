@@ -174,7 +174,23 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     uint64_t* empty_bar = full_bar + STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_tiles = (n_rows + BM - 1) / BM, col_panels = (n_cols + BN - 1) / BN;
-    const long long n_tiles = (long long)row_tiles * col_panels;
+    // symmetric mode (bit 1 of `reserved`; A and B describe the same points): only tiles that reach the diagonal or lie
+    // above it are computed, every entry above the diagonal is also stored at its mirror position
+    const bool sym = ((p.reserved >> 1) & 1) != 0;
+    const long long n_tiles = sym ? (long long)row_tiles * col_panels - (long long)row_tiles * (row_tiles - 1)
+                                  : (long long)row_tiles * col_panels;
+    // tile index -> (row tile, column panel); loop-free (it is also evaluated under the producer's divergent branch)
+    auto tile_coords = [&](long long t, int& pr, int& pc) {
+        if (!sym) { pr = (int)(t / col_panels); pc = (int)(t % col_panels); return; }
+        // row tile r owns col_panels - 2 r tiles; S(r) = r * col_panels - r (r - 1) tiles precede it
+        const double c1 = (double)col_panels + 1.0;
+        int r = (int)(0.5 * (c1 - sqrt(fmax(c1 * c1 - 4.0 * (double)t, 0.0))));
+        r = max(0, min(r, row_tiles - 1));
+        if ((long long)r * col_panels - (long long)r * (r - 1) > t) --r;
+        if (r + 1 < row_tiles && (long long)(r + 1) * col_panels - (long long)(r + 1) * r <= t) ++r;
+        pr = r;
+        pc = 2 * r + (int)(t - ((long long)r * col_panels - (long long)r * (r - 1)));
+    };
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -199,7 +215,8 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         const bool free_slot = wait_hw ? mbar_try_wait_once(&empty_bar[p_stage], p_phase ^ 1)
                                        : mbar_test(&empty_bar[p_stage], p_phase ^ 1);   // first ring pass: immediately true
         if (!free_slot) return false;
-        const int pr = (int)(p_tile / col_panels), pc = (int)(p_tile % col_panels);
+        int pr, pc;
+        tile_coords(p_tile, pr, pc);
         const double* srcA0 = A + ((size_t)(2 * pr) * kg_total + p_group) * (PANEL * 4);   // operands are padded to
         const double* srcA1 = srcA0 + (size_t)kg_total * (PANEL * 4);                       // ROW_PAD rows: both exist
         const double* srcB = B + ((size_t)pc * kg_total + p_group) * (PANEL * 4);
@@ -251,7 +268,8 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     int stage = 0;
     uint32_t phase = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int pr = (int)(t / col_panels), pc = (int)(t % col_panels);
+        int pr, pc;
+        tile_coords(t, pr, pc);
         double acc[NF][4][2][2];
 #pragma unroll
         for (int f = 0; f < NF; ++f)
@@ -323,6 +341,10 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             } else {
                 dst = out + (size_t)row * ld_out + c;
                 pair_ok = vec_ok && ((c & 1) == 0);
+            }
+            if (sym) {          // mirror (row-major only): entries strictly above the diagonal
+                if (col > row) st_cs_f64(out + (size_t)col * ld_out + row, r0);
+                if (col + 1 > row && col + 1 < n_cols) st_cs_f64(out + (size_t)(col + 1) * ld_out + row, r1);
             }
             if (pair_ok && col + 1 < n_cols) st_cs_f64x2(dst, r0, r1);
             else {
@@ -408,7 +430,8 @@ static int launch(const double* A, const double* B, int n_rows, int n_cols, int 
     auto kern = pairwise_kernel<EPI, NF, NV, D>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    const long long tiles = (long long)((n_rows + BM - 1) / BM) * ((n_cols + BN - 1) / BN);
+    const long long rt = (n_rows + BM - 1) / BM, cp = (n_cols + BN - 1) / BN;
+    const long long tiles = ((p.reserved >> 1) & 1) ? rt * cp - rt * (rt - 1) : rt * cp;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, SMEM_BYTES);
     if (per_sm < 1) per_sm = 1;
@@ -428,6 +451,7 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
     if (epi->out_layout == LSK_OUT_ROW_MAJOR && ld_out < n_cols) return LSK_ESIZE;
     if (epi->out_layout == LSK_OUT_PANEL_MAJOR && epi->out_kg < 1) return LSK_ESIZE;
     if (epi->out_layout != LSK_OUT_ROW_MAJOR && epi->out_layout != LSK_OUT_PANEL_MAJOR) return LSK_EARG;
+    if (((epi->reserved >> 1) & 1) && (n_rows != n_cols || epi->out_layout != LSK_OUT_ROW_MAJOR || epi->kind == LSK_EPI_FEAT_CHEB1 || epi->kind == LSK_EPI_FEAT_SPARSE)) return LSK_EARG;
     if (n_rows == 0 || n_cols == 0) return 0;
     if (n_rows > 0x7fffffffLL || n_cols > 0x7fffffffLL) return LSK_ESIZE;
     const LskEpilogue& p = *epi;

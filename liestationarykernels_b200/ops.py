@@ -45,10 +45,16 @@ def embed(plan: GroupPlan, x: torch.Tensor, side: str) -> torch.Tensor:
 
 
 def pairwise_poly(emb_a: torch.Tensor, emb_b: torch.Tensor, n_rows: int, n_cols: int, kg_total: int,
-                  epilogue: _lib.LskEpilogue, out: torch.Tensor | None = None) -> torch.Tensor:
-    """out[i, j] = scale * P(invariants of pair (i, j)) — the fused covariance tile kernel."""
+                  epilogue: _lib.LskEpilogue, out: torch.Tensor | None = None, symmetric: bool = False) -> torch.Tensor:
+    """out[i, j] = scale * P(invariants of pair (i, j)) — the fused covariance tile kernel.
+    symmetric=True (same points on both sides, n_rows == n_cols): only the upper triangle of tiles is computed and
+    mirrored, which halves the work of `kernel(x)` and of a Gram `Phi Phi^T`."""
     _lib.require_cuda()
     lib = _lib.load()
+    if symmetric and n_rows == n_cols and n_rows > 256:
+        epilogue.reserved |= 2
+    else:
+        epilogue.reserved &= ~2
     if out is None:
         out = torch.empty((n_rows, n_cols), dtype=F64, device=emb_a.device)
     else:
@@ -102,7 +108,7 @@ def gram(a: PanelMatrix, b: PanelMatrix, scale: float = 1.0, out: torch.Tensor |
     ep.group_begin[0], ep.group_end[0] = 0, a.kg
     ep.scale = float(scale)
     ep.out_layout = _lib.OUT_ROW_MAJOR
-    return pairwise_poly(a.buf, b.buf, a.rows, b.rows, a.kg, ep, out=out)
+    return pairwise_poly(a.buf, b.buf, a.rows, b.rows, a.kg, ep, out=out, symmetric=(a is b))
 
 
 def class_features(plan: GroupPlan, x: torch.Tensor, phases: torch.Tensor, row_scales, panel: bool):

@@ -101,8 +101,9 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         plan = manifold.plan
         ep = self._epilogue(normalize)
         ea = ops.embed(plan, x, "a")
-        eb = ea if (y is x and not plan.is_complex) else ops.embed(plan, y, "b")
-        return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out)
+        same = y is x and not plan.is_complex
+        eb = ea if same else ops.embed(plan, y, "b")
+        return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 
     # ---- differentiable path ---------------------------------------------------------------------------------
     def _hyper_parameters(self):
@@ -130,8 +131,9 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         plan = manifold.plan
         ep = plan.epilogue(np.asarray(coefs, dtype=np.float64) * manifold._dims, 1.0, form=self.form)
         ea = ops.embed(plan, x, "a")
-        eb = ea if (y is x and not plan.is_complex) else ops.embed(plan, y, "b")
-        return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out)
+        same = y is x and not plan.is_complex
+        eb = ea if same else ops.embed(plan, y, "b")
+        return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 
 
     def _epilogue(self, normalize):

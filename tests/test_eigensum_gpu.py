@@ -111,3 +111,22 @@ def test_large_block_properties():
         g = space.rand(1)
         kc = kern(torch.matmul(g, x[:256]), torch.matmul(g, x[:300]))     # left translation invariance
         assert torch.allclose(kc, k[:256, :300], rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("n", [257, 512, 1000, 2049])
+def test_symmetric_mode_equals_general_mode(n):
+    """kernel(x) takes the upper-triangular fast path; it must equal kernel(x, x.clone()) entry for entry"""
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200 import ops
+    space = _space("SO", 5, 20)
+    kern = EigenbasisSumKernel(_measure(dict(kind="matern", dim=10, lengthscale=1.0, nu=2.5)), space)
+    kern.eval()
+    torch.manual_seed(n)
+    x = space.rand(n)
+    with torch.no_grad():
+        ksym = kern(x)
+        kgen = kern(x, x.clone())
+    assert torch.equal(ksym, kgen)
+    a = torch.randn(n, 100, dtype=torch.float64, device="cuda")
+    pa = ops.PanelMatrix.from_dense(a)
+    assert torch.equal(ops.gram(pa, pa), ops.gram(pa, ops.PanelMatrix.from_dense(a)))
