@@ -14,6 +14,7 @@
 //     entry itself.  Nothing of size N*M*A is ever stored (the reference materialises [N*M*A, n, n]).
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
+#include <cstring>
 
 namespace lsk {
 
@@ -248,6 +249,148 @@ homog_pair_kernel(const double* __restrict__ gx, const double* __restrict__ gy, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// pair kernel, fast variant: the class polynomials are linear in the monomials of the invariants, so the average over
+// the subgroup samples is taken on the MONOMIALS (a fixed, fully unrolled table in registers) and the per-irrep
+// coefficients are applied once per pair instead of once per (pair, sample).  Subgroup samples are staged in shared
+// memory and read as broadcasts.  rank 1: S[a] = mean_k T_a(c_k), a <= AMAX;  rank 2: S[a][b] = mean_k s1^a s2^b.
+// ------------------------------------------------------------------------------------------------------------
+template <int N_, int AMAX, int BMAX>
+__global__ void __launch_bounds__(256)
+homog_pair_kernel_v2(const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ h,
+                     int n_rows, int n_cols, int n_avg, double* __restrict__ out, long long ld_out,
+                     const __grid_constant__ LskEpilogue p)
+{
+    constexpr int RANK = N_ / 2;
+    constexpr int HCHUNK = 64;                                   // subgroup samples staged per pass
+    __shared__ __align__(16) double sh[HCHUNK * N_ * N_ + 2];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    const bool active = (i < n_rows) && (j < n_cols);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    double M[N_][N_];
+    if (active) {
+        double xi[N_][N_], yj[N_][N_];
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                xi[a][b] = gx[(size_t)i * N_ * N_ + a * N_ + b];
+                yj[a][b] = gy[(size_t)j * N_ * N_ + a * N_ + b];
+            }
+        const bool swap = (p.reserved & 1) != 0;
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < N_; ++c) s = swap ? fma(yj[c][a], xi[c][b], s) : fma(xi[c][a], yj[c][b], s);
+                M[a][b] = s;
+            }
+    } else {
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) M[a][b] = 0.0;
+    }
+    double S[(AMAX + 1) * (RANK == 1 ? 1 : BMAX + 1)];
+#pragma unroll
+    for (int q = 0; q < (AMAX + 1) * (RANK == 1 ? 1 : BMAX + 1); ++q) S[q] = 0.0;
+
+    for (int k0 = 0; k0 < n_avg; k0 += HCHUNK) {
+        const int kc = min(HCHUNK, n_avg - k0);
+        __syncthreads();
+        for (int q = tid; q < kc * N_ * N_; q += 256) sh[q] = h[(size_t)k0 * N_ * N_ + q];
+        __syncthreads();
+        for (int k = 0; k < kc; ++k) {
+            const double* hk = sh + k * N_ * N_;
+            double var[RANK];
+            if constexpr (RANK == 1) {
+                double t1 = 0.0;
+#pragma unroll
+                for (int a = 0; a < N_; ++a)
+#pragma unroll
+                    for (int b = 0; b < N_; ++b) t1 = fma(M[a][b], hk[a * N_ + b], t1);
+                var[0] = fma(p.aff[0][1], t1, p.aff[0][0]);
+            } else {
+                double G[N_][N_];
+#pragma unroll
+                for (int b = 0; b < N_; ++b) {
+                    double hb[N_];
+#pragma unroll
+                    for (int c = 0; c < N_; ++c) hb[c] = hk[b * N_ + c];
+#pragma unroll
+                    for (int a = 0; a < N_; ++a) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int c = 0; c < N_; ++c) s = fma(M[a][c], hb[c], s);
+                        G[a][b] = s;
+                    }
+                }
+                double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                for (int a = 0; a < N_; ++a) {
+                    t1 += G[a][a];
+#pragma unroll
+                    for (int b = 0; b < N_; ++b) t2 = fma(G[a][b], G[b][a], t2);
+                }
+                const double e2 = 0.5 * (t1 * t1 - t2);
+                var[0] = fma(p.aff[0][2], e2, fma(p.aff[0][1], t1, p.aff[0][0]));
+                var[1] = fma(p.aff[1][2], e2, fma(p.aff[1][1], t1, p.aff[1][0]));
+            }
+            if constexpr (RANK == 1) {
+                double t0 = 1.0, t1c = var[0];
+                const double x2 = 2.0 * var[0];
+                S[0] += 1.0;
+#pragma unroll
+                for (int a = 1; a <= AMAX; ++a) {
+                    S[a] += t1c;
+                    const double nx = fma(x2, t1c, -t0);
+                    t0 = t1c; t1c = nx;
+                }
+            } else {
+                double pa[AMAX + 1], pb[BMAX + 1];
+                pa[0] = 1.0; pb[0] = 1.0;
+#pragma unroll
+                for (int a = 1; a <= AMAX; ++a) pa[a] = pa[a - 1] * var[0];
+#pragma unroll
+                for (int b = 1; b <= BMAX; ++b) pb[b] = pb[b - 1] * var[1];
+#pragma unroll
+                for (int b = 0; b <= BMAX; ++b)
+#pragma unroll
+                    for (int a = 0; a <= AMAX; ++a) S[b * (AMAX + 1) + a] = fma(pa[a], pb[b], S[b * (AMAX + 1) + a]);
+            }
+        }
+    }
+    if (!active) return;
+    // per-irrep coefficients applied once to the averaged monomials (dynamic exponents -> local array)
+    double Sl[(AMAX + 1) * (RANK == 1 ? 1 : BMAX + 1)];
+    const double inv_avg = p.scale / (double)n_avg;
+#pragma unroll
+    for (int q = 0; q < (AMAX + 1) * (RANK == 1 ? 1 : BMAX + 1); ++q) Sl[q] = S[q] * inv_avg;
+    int pos = 0;
+    for (int l = 0; l < p.nterms; ++l) {
+        const int len = p.row_len[l];
+        double v = 0.0;
+        if constexpr (RANK == 1) {
+            for (int a = 0; a < len; ++a) v = fma(p.coef[pos + a], Sl[a], v);
+        } else {
+            for (int t = 0; t < len; ++t) {
+                const unsigned long long e = (unsigned long long)__double_as_longlong(p.coef[2 * (pos + t) + 1]);
+                const int ea = (int)(e & 0xffu), eb = (int)((e >> 8) & 0xffu);
+                v = fma(p.coef[2 * (pos + t)], Sl[eb * (AMAX + 1) + ea], v);
+            }
+        }
+        pos += len;
+        const long long c = (long long)l * p.feat_stride + j;
+        double* dst = (p.out_layout == LSK_OUT_PANEL_MAJOR)
+            ? out + (((size_t)(i >> 6) * p.out_kg + (size_t)(c >> 2)) * PANEL + (i & 63)) * 4 + (c & 3)
+            : out + (size_t)i * ld_out + c;
+        *dst = v;
+    }
+}
+
 }  // namespace lsk
 
 extern "C" int lsk_lift_frames(const void* x, long long num, int n, int m, void* out, void* bad_count, void* stream) {
@@ -282,10 +425,26 @@ extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const
     double* o = static_cast<double*>(out);
     if (n == 3) {
         if (p.kind != LSK_EPI_FEAT_CHEB1 || tot > LSK_MAX_COEF) return LSK_EARG;
-        homog_pair_kernel<3><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+        int maxlen = 0;
+        for (int l = 0; l < p.nterms; ++l) maxlen = p.row_len[l] > maxlen ? p.row_len[l] : maxlen;
+        if (maxlen <= 16)          // Chebyshev degree <= 15: averaged-monomial kernel
+            homog_pair_kernel_v2<3, 15, 0><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+        else
+            homog_pair_kernel<3><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
     } else if (n == 5) {
         if (p.kind != LSK_EPI_FEAT_SPARSE || 2 * tot > LSK_MAX_COEF) return LSK_EARG;
-        homog_pair_kernel<5><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+        int amax = 0, bmax = 0;
+        for (int t = 0; t < tot; ++t) {
+            unsigned long long e;
+            memcpy(&e, &p.coef[2 * t + 1], 8);
+            const int ea = (int)(e & 0xffu), eb = (int)((e >> 8) & 0xffu);
+            amax = ea > amax ? ea : amax;
+            bmax = eb > bmax ? eb : bmax;
+        }
+        if (amax <= 6 && bmax <= 3)
+            homog_pair_kernel_v2<5, 6, 3><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+        else
+            homog_pair_kernel<5><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
     } else {
         return LSK_EUNSUPPORTED;
     }
