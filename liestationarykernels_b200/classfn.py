@@ -22,6 +22,8 @@ from ._lib import (EPI_CHEB1, EPI_ORBIT2, EPI_SPARSE, EPI_STAIR2, MAX_COEF, MAX_
                    LskEpilogue)
 
 
+HODGE = 4       # embedding part code: Lambda^k x with the Hodge star applied to the row index (csrc/lsk_embed.cu)
+Z_SIGN = {4: -1.0, 8: 1.0}   # z = Z_SIGN * <*Lambda^r x, Lambda^r y>, matching the reference's class labelling
 SPIN5 = 100     # embedding segment code: the 16 rotor coefficients of the Spin(5) lift (csrc/lsk_embed.cu)
 
 
@@ -49,14 +51,20 @@ class GroupPlan:
         n = self.n
         segs_a, segs_b = [], []        # (wedge, part)
         if self.family == "SO":
-            if n % 2 == 0:
-                raise NotImplementedError(
-                    "SO(%d): even special orthogonal groups need the Pfaffian sign invariant, which this build does "
-                    "not provide yet (SURVEY.md 7.3); supported: SO(3), SO(5), SO(7)" % n)
             rank = n // 2
             if rank > 3:
-                raise NotImplementedError("SO(%d): compound matrices beyond Lambda^3 are not implemented" % n)
-            if n == 5 and self.use_spin:
+                raise NotImplementedError("SO(%d): compound matrices beyond Lambda^3 are not implemented "
+                                          "(supported: SO(3) ... SO(7))" % n)
+            if n % 2 == 0:
+                # e_1..e_r from the compound matrices; for even r additionally z = prod 2 sin(theta_i), the invariant that
+                # separates the two SO(2r) classes with equal spectrum, as the Hodge-star form <*Lambda^r x, Lambda^r y>
+                for k in range(1, rank + 1):
+                    segs_a.append((k, 0))
+                    segs_b.append((k, 0))
+                if rank % 2 == 0:
+                    segs_a.append((rank, HODGE))
+                    segs_b.append((rank, 0))
+            elif n == 5 and self.use_spin:
                 # Spin(5) lift: tr g (25-term dot) + the rotor inner product <R_x, R_y> = cos(t1/2) cos(t2/2)
                 # (16-term dot) replace the 100-term Lambda^2 form: K = 44 instead of 128
                 segs_a += [(1, 0), (SPIN5, 0)]
@@ -108,6 +116,10 @@ class GroupPlan:
                 self.M = M
                 self.aff = [[-0.5, 0.5]]
                 return
+            if n % 2 == 0:
+                self.kind = "sparse"
+                self._build_so_even(sigs)
+                return
             monos, mat = inv.character_matrix("SO", n, sigs)
             self.monos = monos
             self.M = np.array(mat, dtype=np.float64)
@@ -143,6 +155,33 @@ class GroupPlan:
         self.M = np.array(mat, dtype=np.float64)
         assert np.all(np.abs(self.M) < 2.0 ** 53)
         self.aff = [[0.0] + [1.0 if f == v else 0.0 for f in range(self.nforms)] for v in range(self.nforms)]
+
+    def _build_so_even(self, sigs):
+        """Re chi = ( P(s) + (-1)^{r/2} z Q(s) ) / 2 for even r, P(s) / 2 for odd r (invariants.so_even_character_polys);
+        variables (s_1..s_r[, z]).  The sign convention of z (which of the two classes with equal spectrum is which) is
+        the reference's `torus_representative` (so.py:151-168); Z_SIGN was fixed against its golden output."""
+        n, r = self.n, self.n // 2
+        with_z = r % 2 == 0
+        polys = []
+        for sgn in sigs:
+            P, Q = inv.so_even_character_polys(n, tuple(sgn))
+            poly = {e + ((0,) if with_z else ()): Fraction(c, 2) for e, c in P.items()}
+            if with_z:
+                for e, c in Q.items():
+                    poly[e + (1,)] = poly.get(e + (1,), 0) + Fraction((-1) ** (r // 2) * c, 2)
+            polys.append(poly)
+        monos = sorted(set().union(*[set(q) for q in polys]))
+        index = {m: i for i, m in enumerate(monos)}
+        M = np.zeros((len(sigs), len(monos)))
+        for l, q in enumerate(polys):
+            for m, c in q.items():
+                M[l, index[m]] = float(c)
+        self.sparse_expo, self.M = monos, M
+        aff = _so_even_affine(n)                       # rows over (1, e_1..e_r)
+        nf = self.nforms
+        self.aff = [row + [0.0] * (1 + nf - len(row)) for row in aff]
+        if with_z:
+            self.aff.append([0.0] * nf + [Z_SIGN[n]])
 
     def _build_stair(self, monos):
         """Layout of the fast (monomial) form for csrc/lsk_pairwise.cu `epi_stair2`: row slot k (evaluation order,
@@ -400,6 +439,41 @@ def _so_odd_affine(n: int):
             for i in range(r + 1):
                 acc[i] -= T[k][j] * sol[j][i]
         assert T[k][k] != 0 and all(T[k][j] == 0 for j in range(k + 1, r + 1))
+        sol[k] = [a / T[k][k] for a in acc]
+        rows.append([float(v) for v in sol[k]])
+    return rows
+
+
+def _so_even_affine(n: int):
+    """Rows [const, coef of e_1, ..., coef of e_r]: s_k(cos theta) as an affine function of e_1..e_r of g in SO(2r).
+    det(zI - g) = prod_i (z^2 - 2 c_i z + 1) = sum_j s_j (-2z)^j (z^2 + 1)^(r - j)."""
+    r = n // 2
+
+    def pmul(a, b):
+        out = [Fraction(0)] * (len(a) + len(b) - 1)
+        for i, x in enumerate(a):
+            for j, y in enumerate(b):
+                out[i + j] += x * y
+        return out
+
+    basis = []
+    for j in range(r + 1):
+        p = [Fraction(1)]
+        for _ in range(j):
+            p = pmul(p, [Fraction(0), Fraction(-2)])
+        for _ in range(r - j):
+            p = pmul(p, [Fraction(1), Fraction(0), Fraction(1)])
+        basis.append(p)
+    T = [[(-1) ** k * (basis[j][n - k] if n - k < len(basis[j]) else Fraction(0)) for j in range(r + 1)] for k in range(r + 1)]
+    sol = {0: [Fraction(1)] + [Fraction(0)] * r}
+    rows = []
+    for k in range(1, r + 1):
+        acc = [Fraction(0)] * (r + 1)
+        acc[k] = Fraction(1)
+        for j in range(k):
+            for i in range(r + 1):
+                acc[i] -= T[k][j] * sol[j][i]
+        assert T[k][k] != 0
         sol[k] = [a / T[k][k] for a in acc]
         rows.append([float(v) for v in sol[k]])
     return rows

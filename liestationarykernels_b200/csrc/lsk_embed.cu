@@ -16,7 +16,7 @@ struct EmbedSpec {
     int nseg;
     int wedge[4];        // 1, 2 or 3
     int part[4];         // 0: real matrix;  1: complex (re, im);  2: complex (re, im) [B side, real form];
-                         // 3: complex (-im, re) [B side, imaginary form]
+                         // 3: complex (-im, re) [B side, imaginary form];  4: real, Hodge star on the row index (n = 2k)
     int group_begin[4];  // first k-group of the segment
     int length[4];       // number of doubles in the segment (before padding to a multiple of 4)
 };
@@ -146,9 +146,25 @@ embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, E
                 int I[3] = {0, 0, 0}, J[3] = {0, 0, 0};
                 unrank(el / C, n, k, I);
                 unrank(el % C, n, k, J);
+                double hodge = 1.0;
+                if (!CPLX && part == 4) {
+                    // Hodge star on the row index (n = 2k): I -> complement I^c, sign of the permutation (I, I^c)
+                    int comp[3] = {0, 0, 0}, nc = 0, inv = 0;
+                    for (int v = 0; v < n; ++v) {
+                        bool in = false;
+                        for (int q = 0; q < k; ++q) in = in || (I[q] == v);
+                        if (!in) {
+                            for (int q = 0; q < k; ++q) inv += (I[q] > v);      // inversions between I and I^c
+                            if (nc < 3) comp[nc] = v;
+                            ++nc;
+                        }
+                    }
+                    hodge = (inv & 1) ? -1.0 : 1.0;
+                    for (int q = 0; q < 3; ++q) I[q] = comp[q];
+                }
                 double re, im;
                 minor<CPLX>(x + row * (long long)(CPLX ? 2 : 1) * n * n, n, k, I, J, re, im);
-                if (!CPLX) val = re;
+                if (!CPLX) val = hodge * re;
                 else if (part == 3) val = (e & 1) ? re : -im;
                 else val = (e & 1) ? im : re;
             }
@@ -196,7 +212,7 @@ extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_comp
             continue;
         }
         if (wedge[s] < 1 || wedge[s] > 3 || wedge[s] > n) return LSK_EARG;
-        if (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0)) return LSK_EARG;
+        if (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0 && !(part[s] == 4 && n == 2 * wedge[s]))) return LSK_EARG;
         int c = 1;
         for (int i = 1; i <= wedge[s]; ++i) c = c * (n - wedge[s] + i) / i;
         spec.wedge[s] = wedge[s]; spec.part[s] = part[s]; spec.group_begin[s] = group_begin[s];

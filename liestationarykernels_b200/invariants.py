@@ -157,6 +157,60 @@ def su_character_poly(n: int, signature: tuple) -> dict:
     return {k: v for k, v in out.items() if v}
 
 
+@lru_cache(maxsize=None)
+def cheb_U(k: int) -> tuple:
+    """Coefficients (low -> high) of the Chebyshev polynomial of the second kind, sin((k+1) t) = sin t U_k(cos t)."""
+    if k == 0:
+        return (1,)
+    if k == 1:
+        return (0, 2)
+    a, b = cheb_U(k - 1), cheb_U(k - 2)
+    out = [0] * (k + 1)
+    for i, v in enumerate(a):
+        out[i + 1] += 2 * v
+    for i, v in enumerate(b):
+        out[i] -= v
+    return tuple(out)
+
+
+def _sin_orbit_poly(mu, r: int) -> dict:
+    """sum over distinct permutations p of mu (all entries > 0) of prod_i U_{p_i - 1}(c_i), a symmetric polynomial in c.
+    With prod_i (2 i sin theta_i) in front it is the sign-weighted sum over the hyperoctahedral orbit of mu."""
+    out = {}
+    for p in set(itertools.permutations(mu)):
+        term = {tuple([0] * r): 1}
+        for i, m in enumerate(p):
+            u = cheb_U(m - 1)
+            f = {tuple(d if j == i else 0 for j in range(r)): c for d, c in enumerate(u) if c}
+            term = p_mul(term, f)
+        out = p_add(out, term)
+    return out
+
+
+@lru_cache(maxsize=None)
+def so_even_character_polys(n: int, signature: tuple):
+    """chi_signature of SO(n), n = 2r even, as  ( P(s) + i^r z Q(s) ) / 2  with s_k = e_k(cos theta) and
+    z = prod_i 2 sin theta_i (the invariant that separates the two SO(2r) classes with the same spectrum).
+    Returns (2P, 2Q) as {exponents over (s_1..s_r): int}.  For odd r the z-term is purely imaginary and drops out of
+    Re chi, which is all the kernels use."""
+    assert n % 2 == 0
+    r = n // 2
+    dom = ch.dominant_weight_multiplicities("D", tuple(signature))
+    P, Q = {}, {}
+    for mu, m in dom.items():
+        amu = tuple(sorted((abs(v) for v in mu), reverse=True))
+        cos_part = dict(symmetric_to_elementary(_cos_orbit_poly(amu, r), r))
+        if all(v != 0 for v in mu):
+            # W(D_r) mu is half of the hyperoctahedral orbit: (Omega_B + sgn * Xi) / 2
+            P = p_add(P, cos_part, m)
+            sgn = 1 if mu[-1] > 0 else -1
+            sin_part = dict(symmetric_to_elementary(_sin_orbit_poly(amu, r), r))
+            Q = p_add(Q, sin_part, m * sgn)
+        else:
+            P = p_add(P, cos_part, 2 * m)
+    return P, Q
+
+
 def character_poly(group: str, n: int, signature) -> dict:
     if group == "SO":
         if n % 2 == 1:

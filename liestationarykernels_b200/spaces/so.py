@@ -70,7 +70,18 @@ class SO(CompactLieGroup):
             order = torch.sort(torch.view_as_real(ev), dim=-2).indices[..., 0]
             ev = torch.gather(ev, dim=-1, index=order)
             return ev[..., 0:-1:2]
-        raise NotImplementedError("SO(%d): even n needs the eigenvector sign trick (so.py:151-168); not provided" % n)
+        # even n: each spectrum belongs to two conjugacy classes; the reference separates them with the orientation of
+        # the eigenvector frame (so.py:151-168).  Same construction here (API-compatibility path only).
+        ev, vec = torch.linalg.eig(x)
+        order = torch.sort(torch.view_as_real(ev), dim=-2).indices[..., 0]
+        ev = torch.gather(ev, dim=-1, index=order)
+        vec = torch.gather(vec, dim=-1, index=order.unsqueeze(-2).broadcast_to(vec.shape))
+        frame = torch.zeros_like(vec)
+        frame[..., ::2] = vec[..., ::2] + vec[..., 1::2]
+        frame[..., 1::2] = vec[..., ::2] - vec[..., 1::2]
+        frame = (frame.real + frame.imag) / math.sqrt(2)
+        first = torch.pow(ev[..., 0], torch.det(frame).sgn())
+        return torch.cat((first.unsqueeze(-1), ev[..., 2::2]), dim=-1)
 
     def pairwise_dist(self, x, y):
         emb = self.pairwise_embed(x, y)

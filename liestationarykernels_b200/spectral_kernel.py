@@ -101,7 +101,7 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         plan = manifold.plan
         ep = self._epilogue(normalize)
         ea = ops.embed(plan, x, "a")
-        same = y is x and not plan.is_complex
+        same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides
         eb = ea if same else ops.embed(plan, y, "b")
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 
@@ -131,7 +131,7 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         plan = manifold.plan
         ep = plan.epilogue(np.asarray(coefs, dtype=np.float64) * manifold._dims, 1.0, form=self.form)
         ea = ops.embed(plan, x, "a")
-        same = y is x and not plan.is_complex
+        same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides
         eb = ea if same else ops.embed(plan, y, "b")
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 

@@ -67,8 +67,23 @@ def embed(plan, x, side):
         if k == 100:
             cols.append(np.stack([spin5_rotor(xi) for xi in x]))
             continue
-        c = compound(x, k).reshape(x.shape[0], -1)
-        if part == 0:
+        c = compound(x, k)
+        if part == 4:                       # Hodge star on the row index: (I, J) -> sign(I, I^c) * minor(I^c, J)
+            n = x.shape[-1]
+            idx = list(itertools.combinations(range(n), k))
+            star = np.zeros_like(c)
+            for a, I in enumerate(idx):
+                comp = tuple(v for v in range(n) if v not in I)
+                perm = list(I) + list(comp)
+                sign = 1
+                for i in range(n):
+                    for j in range(i + 1, n):
+                        if perm[i] > perm[j]:
+                            sign = -sign
+                star[:, a, :] = sign * c[:, idx.index(comp), :]
+            c = star
+        c = c.reshape(x.shape[0], -1)
+        if part == 0 or part == 4:
             v = c.real
         else:
             if part == 3:
