@@ -101,9 +101,9 @@ int lsk_lift_frames(const void* x, long long num, int n, int m, void* out, void*
 
 /* Homogeneous-space pair kernel: for all (i, j), mean over subgroup samples h_k of the class polynomials at
  * lift(x_i)^T lift(y_j) h_k^T.  Replaces CompactHomogeneousSpace.pairwise_diff/pairwise_embed and
- * AveragedLieGroupCharacter.forward (reference space.py:125-135, 273-275).  n in {3, 5}.
+ * AveragedLieGroupCharacter.forward (reference space.py:125-135, 273-275).  n in {3, 4, 5}.
  * lifted_x: [n_rows, n, n], lifted_y: [n_cols, n, n], h_samples: [n_avg, n, n]; epi kind FEAT_CHEB1 (n = 3) or
- * FEAT_SPARSE (n = 5) with one row per output (irrep, or a single collapsed polynomial). */
+ * FEAT_SPARSE (n = 4: variables s_1, s_2, z;  n = 5: s_1, s_2) with one row per output (irrep, or a single collapsed polynomial). */
 int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const void* h_samples, long long n_rows, long long n_cols,
                     int n, int n_avg, const LskEpilogue* epi, void* out, long long ld_out, void* stream);
 

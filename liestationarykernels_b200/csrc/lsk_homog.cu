@@ -143,14 +143,15 @@ __device__ __forceinline__ double eval_cheb_row(const double* coef, int nterms, 
     return fma(x, b1, coef[0] - b2);
 }
 
-// N_: matrix size (3 or 5);  rank = N_ / 2 invariants.  blockDim = (32, 8): x = column j (fastest), y = row i.
+// N_: matrix size (3, 4 or 5).  Invariants: tr g (n = 3);  tr g, e_2(g) (n = 5);  tr g, e_2(g), tr(* Lambda^2 g) (n = 4: the
+// Hodge-star form separates the two SO(4) classes with equal spectrum).  blockDim = (32, 8): x = column j (fastest), y = row i.
 template <int N_>
 __global__ void __launch_bounds__(256)
 homog_pair_kernel(const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ h,
                   int n_rows, int n_cols, int n_avg, double* __restrict__ out, long long ld_out,
                   const __grid_constant__ LskEpilogue p)
 {
-    constexpr int RANK = N_ / 2;
+    constexpr int RANK = (N_ == 3) ? 1 : (N_ == 4 ? 3 : 2);      // number of invariants / polynomial variables
     const int j = blockIdx.x * 32 + threadIdx.x;
     const int i = blockIdx.y * 8 + threadIdx.y;
     if (i >= n_rows || j >= n_cols) return;
@@ -216,6 +217,11 @@ homog_pair_kernel(const double* __restrict__ gx, const double* __restrict__ gy, 
             }
             form[0] = t1;
             form[1] = 0.5 * (t1 * t1 - t2);                      // e_2(g)
+            if constexpr (N_ == 4) {
+                // tr(* Lambda^2 g) = sum_I sign(I, I^c) minor(rows I^c, cols I)
+                auto mn = [&](int r0, int r1, int c0, int c1) { return G[r0][c0] * G[r1][c1] - G[r0][c1] * G[r1][c0]; };
+                form[2] = mn(2, 3, 0, 1) + mn(0, 1, 2, 3) - mn(1, 3, 0, 2) - mn(0, 2, 1, 3) + mn(1, 2, 0, 3) + mn(0, 3, 1, 2);
+            }
         }
         double var[RANK];
 #pragma unroll
@@ -431,6 +437,9 @@ extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const
             homog_pair_kernel_v2<3, 15, 0><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
         else
             homog_pair_kernel<3><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+    } else if (n == 4) {
+        if (p.kind != LSK_EPI_FEAT_SPARSE || 2 * tot > LSK_MAX_COEF) return LSK_EARG;
+        homog_pair_kernel<4><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
     } else if (n == 5) {
         if (p.kind != LSK_EPI_FEAT_SPARSE || 2 * tot > LSK_MAX_COEF) return LSK_EARG;
         int amax = 0, bmax = 0;

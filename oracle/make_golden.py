@@ -133,6 +133,10 @@ def main(only=None):
         ("homog_grassmannian52", Grassmannian, (5, 2), dict(order=10, average_order=20), dict(kind="heat", dim=6, lengthscale=1.0), 12, 8),
         ("homog_orgrassmannian52", OrientedGrassmannian, (5, 2), dict(order=10, average_order=16), dict(kind="heat", dim=6, lengthscale=1.0), 12, 8),
         ("homog_stiefel32", Stiefel, (3, 2), dict(order=10, average_order=10), dict(kind="heat", dim=3, lengthscale=1.0), 12, 8),
+        ("homog_stiefel42", Stiefel, (4, 2), dict(order=10, average_order=12), dict(kind="heat", dim=5, lengthscale=1.0), 12, 8),
+        ("homog_grassmannian42", Grassmannian, (4, 2), dict(order=10, average_order=12), dict(kind="heat", dim=4, lengthscale=1.0), 12, 8),
+        ("homog_orgrassmannian42", OrientedGrassmannian, (4, 2), dict(order=10, average_order=12), dict(kind="heat", dim=4, lengthscale=1.0), 12, 8),
+        ("homog_grassmannian31", Grassmannian, (3, 1), dict(order=10, average_order=10), dict(kind="heat", dim=2, lengthscale=1.0), 12, 8),
     ]
     for name, cls, nm, kw, mspec, nx, nph in hom_cases:
         if not want(name):

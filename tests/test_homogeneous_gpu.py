@@ -8,7 +8,8 @@ from conftest import load_golden, scaled_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
-CASES = ["homog_stiefel53", "homog_stiefel52_heat", "homog_grassmannian52", "homog_orgrassmannian52", "homog_stiefel32"]
+CASES = ["homog_stiefel53", "homog_stiefel52_heat", "homog_grassmannian52", "homog_orgrassmannian52", "homog_stiefel32",
+         "homog_stiefel42", "homog_grassmannian42", "homog_orgrassmannian42", "homog_grassmannian31"]
 
 
 def _measure(spec):

@@ -69,7 +69,9 @@ def test_rand_replays_reference_rng():
 
 
 HOM = {"homog_stiefel53": "stiefel", "homog_stiefel52_heat": "stiefel", "homog_grassmannian52": "grassmannian",
-       "homog_orgrassmannian52": "oriented_grassmannian", "homog_stiefel32": "stiefel"}
+       "homog_orgrassmannian52": "oriented_grassmannian", "homog_stiefel32": "stiefel", "homog_stiefel42": "stiefel",
+       "homog_grassmannian42": "grassmannian", "homog_orgrassmannian42": "oriented_grassmannian",
+       "homog_grassmannian31": "grassmannian"}
 
 
 @pytest.mark.parametrize("name", list(HOM))
