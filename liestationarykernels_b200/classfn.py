@@ -192,7 +192,7 @@ class GroupPlan:
             rows[b] = max(rows.get(b, -1), a)
         nrows = max(rows) + 1
         self.stair_rows = [max(2, (rows.get(b, 0) + 2) // 2 * 2) for b in range(nrows)]
-        self.stair_ok = nrows <= 16 and max(self.stair_rows) <= 16
+        self.stair_ok = nrows <= 12 and max(self.stair_rows) <= 16      # LSK_STAIR_MAX_ROWS / LSK_STAIR_STRIDE
         index = {m: i for i, m in enumerate(monos)}
         self.stair_slots = []            # (offset in coef[], monomial index or -1)
         self.stair_shape = 0

@@ -83,43 +83,70 @@ __device__ void minor(const double* x, int n, int k, const int (&I)[3], const in
 //     < R(x), R(y) > = +- cos(theta_1 / 2) cos(theta_2 / 2)
 // (the character of the 4-dimensional spin representation / 4), which together with tr g determines the class of g.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double blade_sign(int a, int b) {
+__host__ __device__ constexpr double blade_sign(int a, int b) {
     int s = 0;
     a >>= 1;
-    while (a) { s += __popc(a & b); a >>= 1; }
+    while (a) {
+        int t = a & b, c = 0;
+        while (t) { c += t & 1; t >>= 1; }
+        s += c;
+        a >>= 1;
+    }
     return (s & 1) ? -1.0 : 1.0;
 }
+__host__ __device__ constexpr int even_mask(int k) {          // even-parity 5-bit mask A with A >> 1 == k
+    int c = 0, t = k;
+    while (t) { c += t & 1; t >>= 1; }
+    return (k << 1) | (c & 1);
+}
 
-__device__ void spin5_rotor(const double* __restrict__ x, double (&R)[16]) {
+// R <- R * (ch - sh e_J e_I): all blade indices and signs are compile-time constants, everything stays in registers
+template <int J, int I>
+__device__ __forceinline__ void rotor_step(double (&m)[5][5], double (&R)[16]) {
+    const double a = m[J][J], b = m[I][J];
+    const double r = hypot(a, b);
+    if (r == 0.0) return;
+    const double c = a / r, s = b / r;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double rj = m[J][k], ri = m[I][k];
+        m[J][k] = c * rj + s * ri;
+        m[I][k] = -s * rj + c * ri;
+    }
+    double ch, sh;                       // half-angle, formed without cancellation
+    if (c >= 0.0) { ch = sqrt(0.5 * (1.0 + c)); sh = s / (2.0 * ch); }
+    else { sh = (s >= 0.0 ? 1.0 : -1.0) * sqrt(0.5 * (1.0 - c)); ch = s / (2.0 * sh); }
+    constexpr int B = (1 << J) | (1 << I);
+    double nw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        // target blade k receives ch * R[k] and -sh * sign * R[src] with src = k ^ (B >> 1) adjusted for parity
+        constexpr int dummy = 0; (void)dummy;
+        nw[k] = ch * R[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int A = even_mask(k);
+        const int dst = (A ^ B) >> 1;
+        nw[dst] = fma(-sh * blade_sign(A, B), R[k], nw[dst]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) R[k] = nw[k];
+}
+
+__device__ __forceinline__ void spin5_rotor(const double* __restrict__ x, double (&R)[16]) {
     double m[5][5];
+#pragma unroll
     for (int r = 0; r < 5; ++r)
+#pragma unroll
         for (int c = 0; c < 5; ++c) m[r][c] = x[r * 5 + c];
+#pragma unroll
     for (int k = 0; k < 16; ++k) R[k] = 0.0;
     R[0] = 1.0;
-    for (int j = 0; j < 4; ++j) {
-        for (int i = j + 1; i < 5; ++i) {
-            const double a = m[j][j], b = m[i][j];
-            const double r = hypot(a, b);
-            if (r == 0.0) continue;
-            const double c = a / r, s = b / r;
-            for (int k = 0; k < 5; ++k) {
-                const double rj = m[j][k], ri = m[i][k];
-                m[j][k] = c * rj + s * ri;
-                m[i][k] = -s * rj + c * ri;
-            }
-            double ch, sh;                       // half-angle, formed without cancellation
-            if (c >= 0.0) { ch = sqrt(0.5 * (1.0 + c)); sh = s / (2.0 * ch); }
-            else { sh = (s >= 0.0 ? 1.0 : -1.0) * sqrt(0.5 * (1.0 - c)); ch = s / (2.0 * sh); }
-            const int B = (1 << j) | (1 << i);
-            double nw[16];
-            for (int k = 0; k < 16; ++k) nw[k] = ch * R[k];
-            for (int k = 0; k < 16; ++k) {
-                const int A = (k << 1) | (__popc(k) & 1);          // even-parity 5-bit mask with A >> 1 == k
-                nw[(A ^ B) >> 1] += -sh * blade_sign(A, B) * R[k];
-            }
-            for (int k = 0; k < 16; ++k) R[k] = nw[k];
-        }
-    }
+    rotor_step<0, 1>(m, R); rotor_step<0, 2>(m, R); rotor_step<0, 3>(m, R); rotor_step<0, 4>(m, R);
+    rotor_step<1, 2>(m, R); rotor_step<1, 3>(m, R); rotor_step<1, 4>(m, R);
+    rotor_step<2, 3>(m, R); rotor_step<2, 4>(m, R);
+    rotor_step<3, 4>(m, R);
 }
 
 template <bool CPLX>
@@ -173,15 +200,30 @@ embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, E
     }
 }
 
-// one thread per point: rotor of the Spin(5) lift into k-groups [g0, g0 + 4) of the panel-major buffer
+// one thread per point: rotor of the Spin(5) lift into k-groups [g0, g0 + 4) of the panel-major buffer; with
+// WITH_MATRIX the same thread also writes the matrix itself (25 values + 3 zeros) into k-groups [gm, gm + 7), which
+// makes this kernel the whole SO(5) embedding (one launch per operand)
+template <bool WITH_MATRIX>
 __global__ void __launch_bounds__(128)
-spin5_embed_kernel(const double* __restrict__ x, long long num, int kg_total, int g0, double* __restrict__ out) {
+spin5_embed_kernel(const double* __restrict__ x, long long num, int kg_total, int g0, int gm, double* __restrict__ out) {
     const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_padded) return;
     double R[16];
     if (row < num) spin5_rotor(x + row * 25, R);
     else for (int k = 0; k < 16; ++k) R[k] = 0.0;
+    if (WITH_MATRIX) {
+        double v[28];
+#pragma unroll
+        for (int k = 0; k < 28; ++k) v[k] = (k < 25 && row < num) ? x[row * 25 + k] : 0.0;
+        double* mb = out + ((row >> 6) * kg_total + gm) * (PANEL * 4) + (row & 63) * 4;
+#pragma unroll
+        for (int g = 0; g < 7; ++g) {
+            double2* dst = reinterpret_cast<double2*>(mb + (size_t)g * (PANEL * 4));
+            dst[0] = make_double2(v[4 * g], v[4 * g + 1]);
+            dst[1] = make_double2(v[4 * g + 2], v[4 * g + 3]);
+        }
+    }
     double* base = out + ((row >> 6) * kg_total + g0) * (PANEL * 4) + (row & 63) * 4;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -225,13 +267,21 @@ extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_comp
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!is_complex && n == 5 && nseg == 2 && spec.wedge[0] == 1 && spec.wedge[1] == LSK_SEG_SPIN5 &&
+        spec.group_begin[0] == 0 && spec.group_begin[1] == 7 && kg_total == 11) {
+        // the standard SO(5) layout [matrix | rotor]: one fused launch
+        const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
+        spin5_embed_kernel<true><<<(unsigned)((rows_padded + 127) / 128), 128, 0, st>>>(
+            static_cast<const double*>(x), num, kg_total, 7, 0, static_cast<double*>(out));
+        return (int)cudaGetLastError();
+    }
     if (is_complex) embed_kernel<true><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
     else embed_kernel<false><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
     for (int s = 0; s < nseg; ++s) {
         if (spec.wedge[s] == LSK_SEG_SPIN5) {
             const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
-            spin5_embed_kernel<<<(unsigned)((rows_padded + 127) / 128), 128, 0, st>>>(
-                static_cast<const double*>(x), num, kg_total, spec.group_begin[s], static_cast<double*>(out));
+            spin5_embed_kernel<false><<<(unsigned)((rows_padded + 127) / 128), 128, 0, st>>>(
+                static_cast<const double*>(x), num, kg_total, spec.group_begin[s], 0, static_cast<double*>(out));
         }
     }
     return (int)cudaGetLastError();

@@ -71,7 +71,7 @@ __device__ __forceinline__ void epi_stair2(const LskEpilogue& p, const double (&
 #pragma unroll
                 for (int r = 0; r < R; ++r) inner[r] = fma(s1[r], c0, c1);
             }
-#pragma unroll 2
+#pragma unroll 1          // code size: 16 row copies x 2 tile halves must stay inside the instruction cache
             for (int q = 1; q < pairs; ++q) {
                 const double c0 = p.coef[LSK_STAIR_STRIDE * k + 2 * q], c1 = p.coef[LSK_STAIR_STRIDE * k + 2 * q + 1];
 #pragma unroll
@@ -160,7 +160,7 @@ __device__ __forceinline__ int chunk_len(int remaining) {
 // main kernel
 //   EPI: epilogue kind;  NF: number of bilinear forms;  NV: number of variables (SPARSE only);  D: ORBIT2 size
 // ------------------------------------------------------------------------------------------------------------
-template <int EPI, int NF, int NV, int D>
+template <int EPI, int NF, int NV, int D, bool SYM>
 __global__ void __launch_bounds__(THREADS, 1)
 pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 int n_rows, int n_cols, int kg_total,               // kg_total: k-groups per row of A and B
@@ -176,12 +176,12 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     const int row_tiles = (n_rows + BM - 1) / BM, col_panels = (n_cols + BN - 1) / BN;
     // symmetric mode (bit 1 of `reserved`; A and B describe the same points): only tiles that reach the diagonal or lie
     // above it are computed, every entry above the diagonal is also stored at its mirror position
-    const bool sym = ((p.reserved >> 1) & 1) != 0;
+    constexpr bool sym = SYM;        // compile-time: the general kernel carries none of the triangular-schedule code
     const long long n_tiles = sym ? (long long)row_tiles * col_panels - (long long)row_tiles * (row_tiles - 1)
                                   : (long long)row_tiles * col_panels;
     // tile index -> (row tile, column panel); loop-free (it is also evaluated under the producer's divergent branch)
     auto tile_coords = [&](long long t, int& pr, int& pc) {
-        if (!sym) { pr = (int)(t / col_panels); pc = (int)(t % col_panels); return; }
+        if constexpr (!SYM) { pr = (int)(t / col_panels); pc = (int)(t % col_panels); return; }
         // row tile r owns col_panels - 2 r tiles; S(r) = r * col_panels - r (r - 1) tiles precede it
         const double c1 = (double)col_panels + 1.0;
         int r = (int)(0.5 * (c1 - sqrt(fmax(c1 * c1 - 4.0 * (double)t, 0.0))));
@@ -239,7 +239,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     auto produce_ahead = [&]() {
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int k = 0; k < STAGES; ++k)
+            for (int k = 0; k < 2; ++k)          // two attempts per call site keep the ring full and the code small
                 if (issued_ahead < STAGES) produce_once(false);
         }
     };
@@ -342,7 +342,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 dst = out + (size_t)row * ld_out + c;
                 pair_ok = vec_ok && ((c & 1) == 0);
             }
-            if (sym) {          // mirror (row-major only): entries strictly above the diagonal
+            if constexpr (SYM) {          // mirror (row-major only): entries strictly above the diagonal
                 if (col > row) st_cs_f64(out + (size_t)col * ld_out + row, r0);
                 if (col + 1 > row && col + 1 < n_cols) st_cs_f64(out + (size_t)(col + 1) * ld_out + row, r1);
             }
@@ -424,14 +424,14 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     }
 }
 
-template <int EPI, int NF, int NV, int D>
+template <int EPI, int NF, int NV, int D, bool SYM = false>
 static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                   const LskEpilogue& p, int max_ctas, cudaStream_t stream) {
-    auto kern = pairwise_kernel<EPI, NF, NV, D>;
+    auto kern = pairwise_kernel<EPI, NF, NV, D, SYM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const long long rt = (n_rows + BM - 1) / BM, cp = (n_cols + BN - 1) / BN;
-    const long long tiles = ((p.reserved >> 1) & 1) ? rt * cp - rt * (rt - 1) : rt * cp;
+    const long long tiles = SYM ? rt * cp - rt * (rt - 1) : rt * cp;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, SMEM_BYTES);
     if (per_sm < 1) per_sm = 1;
@@ -451,7 +451,7 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
     if (epi->out_layout == LSK_OUT_ROW_MAJOR && ld_out < n_cols) return LSK_ESIZE;
     if (epi->out_layout == LSK_OUT_PANEL_MAJOR && epi->out_kg < 1) return LSK_ESIZE;
     if (epi->out_layout != LSK_OUT_ROW_MAJOR && epi->out_layout != LSK_OUT_PANEL_MAJOR) return LSK_EARG;
-    if (((epi->reserved >> 1) & 1) && (n_rows != n_cols || epi->out_layout != LSK_OUT_ROW_MAJOR || epi->kind == LSK_EPI_FEAT_CHEB1 || epi->kind == LSK_EPI_FEAT_SPARSE)) return LSK_EARG;
+    if (((epi->reserved >> 1) & 1) && (n_rows != n_cols || epi->out_layout != LSK_OUT_ROW_MAJOR)) return LSK_EARG;
     if (n_rows == 0 || n_cols == 0) return 0;
     if (n_rows > 0x7fffffffLL || n_cols > 0x7fffffffLL) return LSK_ESIZE;
     const LskEpilogue& p = *epi;
@@ -474,10 +474,13 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
     const int nr = (int)n_rows, nc = (int)n_cols;
 
 #define LSK_GO(EPI, NF, NV, D) return launch<EPI, NF, NV, D>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st)
+#define LSK_GO_SYM(EPI, NF, NV, D) do { if (want_sym) return launch<EPI, NF, NV, D, true>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st); \
+                                        return launch<EPI, NF, NV, D, false>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st); } while (0)
+    const bool want_sym = ((p.reserved >> 1) & 1) != 0;
     switch (p.kind) {
     case LSK_EPI_CHEB1:
         if (p.nterms < 1 || p.nterms > LSK_MAX_COEF || p.nvars != 1) return LSK_EARG;
-        if (p.nforms == 1) LSK_GO(LSK_EPI_CHEB1, 1, 1, 1);
+        if (p.nforms == 1) LSK_GO_SYM(LSK_EPI_CHEB1, 1, 1, 1);
         return LSK_EUNSUPPORTED;
     case LSK_EPI_STAIR2: {
         if (p.nterms < 1 || p.nterms > LSK_STAIR_MAX_ROWS || p.nvars != 2) return LSK_EARG;
@@ -485,7 +488,7 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
             const int pairs = (int)((p.stair_shape >> (4 * k)) & 15ull);
             if (k < p.nterms ? (pairs < 1 || 2 * pairs > LSK_STAIR_STRIDE || p.row_len[k] != 2 * pairs) : pairs != 0) return LSK_EARG;
         }
-        if (p.nforms == 2) LSK_GO(LSK_EPI_STAIR2, 2, 2, 1);
+        if (p.nforms == 2) LSK_GO_SYM(LSK_EPI_STAIR2, 2, 2, 1);
         return LSK_EUNSUPPORTED;
     }
     case LSK_EPI_ORBIT2:
@@ -503,7 +506,7 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_SPARSE, 4, 4, 1);
         return LSK_EUNSUPPORTED;
     case LSK_EPI_LINEAR:
-        if (p.nforms == 1 && p.nvars == 1) LSK_GO(LSK_EPI_LINEAR, 1, 1, 1);
+        if (p.nforms == 1 && p.nvars == 1) LSK_GO_SYM(LSK_EPI_LINEAR, 1, 1, 1);
         return LSK_EARG;
     case LSK_EPI_FEAT_CHEB1:
     case LSK_EPI_FEAT_SPARSE: {
@@ -524,4 +527,5 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         return LSK_EARG;
     }
 #undef LSK_GO
+#undef LSK_GO_SYM
 }

@@ -6,7 +6,7 @@
 #define LSK_MAX_VARS 4
 #define LSK_MAX_COEF 400
 #define LSK_MAX_ROWS 24
-#define LSK_STAIR_MAX_ROWS 16    // STAIR2: rows sit at a fixed stride of LSK_STAIR_STRIDE coefficients
+#define LSK_STAIR_MAX_ROWS 12    // STAIR2: rows sit at a fixed stride of LSK_STAIR_STRIDE coefficients
 #define LSK_STAIR_STRIDE 16
 
 // Epilogue kinds: how the class function is evaluated from the conjugation invariants.
