@@ -5,7 +5,9 @@
  *   - is `extern "C"`, takes plain pointers and sizes, returns int: 0 ok, < 0 argument error (LSK_E*), > 0 cudaError_t;
  *   - takes DEVICE pointers for bulk data (contiguous, row-major float64 unless stated; complex128 = interleaved re,im),
  *     caller-owned, 16-byte aligned; small descriptors (`LskEpilogue`, int arrays) are HOST pointers read during the call;
- *   - launches asynchronously on the `cudaStream_t` passed as `void* stream` (NULL = default stream);
+ *   - launches asynchronously on the `cudaStream_t` passed as `void* stream` (NULL = default stream); the embedding and
+ *     pairwise kernels are launched with programmatic stream serialisation and wait (griddepcontrol.wait) for the previous
+ *     kernel of the stream before their first global-memory access, so ordinary stream semantics hold for the caller;
  *   - allocates nothing that outlives the call and keeps no mutable global state (safe from several host threads on
  *     distinct streams).
  * "reference" citations are paths below /root/reference/src/lie_stationary_kernels/.
@@ -83,6 +85,12 @@ long long lsk_embed_buffer_doubles(long long num, int kg_total);
  * replaces the 100-term Lambda^2 form for SO(5). */
 int lsk_embed_points(const void* x, long long num, int n, int is_complex, int nseg, const int* wedge, const int* part,
                      const int* group_begin, int kg_total, void* out, void* stream);
+
+/* Both operands of one pairwise problem with a single launch (x: side A, y: side B; same n, wedge, group_begin, kg_total;
+ * part_x / part_y as `part` above).  kernel(x, y) = this + lsk_pairwise_poly: two launches per covariance. */
+int lsk_embed_points2(const void* x, long long num_x, const int* part_x, void* out_x,
+                      const void* y, long long num_y, const int* part_y, void* out_y,
+                      int n, int is_complex, int nseg, const int* wedge, const int* group_begin, int kg_total, void* stream);
 
 /* Fused pairwise kernel: bilinear forms on the fp64 tensor-core path + class-polynomial epilogue + store.
  * Replaces, for all N*M pairs, pairwise_embed + the character loop + the weighted sum:

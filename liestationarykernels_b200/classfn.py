@@ -186,7 +186,8 @@ class GroupPlan:
     def _build_stair(self, monos):
         """Layout of the fast (monomial) form for csrc/lsk_pairwise.cu `epi_stair2`: row slot k (evaluation order,
         highest power of s2 first) holds sum_a C[b][a] s1^a, highest a first, padded with zeros at the high end to an
-        even number of coefficients, at the fixed offset 16 k; the pair counts go into a 64-bit shape word."""
+        even number of coefficients, at the fixed offset 16 k; the pair counts go into a 64-bit shape word (4 bits per
+        slot; bit 48 + slot flags a row whose first coefficient is that padding)."""
         rows = {}
         for (a, b) in monos:
             rows[b] = max(rows.get(b, -1), a)
@@ -200,6 +201,8 @@ class GroupPlan:
             ln = self.stair_rows[b]
             if self.stair_ok:
                 self.stair_shape |= (ln // 2) << (4 * slot)
+                if (rows.get(b, 0) + 1) % 2:            # odd row: the slot's first coefficient is padding (bit 48 + slot);
+                    self.stair_shape |= 1 << (48 + slot)   # only the shape-specialised kernel instantiations read this
             for pos, a in enumerate(range(ln - 1, -1, -1)):
                 self.stair_slots.append((16 * slot + pos, index.get((a, b), -1)))
 

@@ -101,4 +101,22 @@ __device__ __forceinline__ void st_cs_f64(double* p, double a) {
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
 }
 
+// programmatic dependent launch (PDL): a kernel launched with `launch_pdl` may start while the previous kernel of the
+// stream is still draining; it must execute pdl_wait() before its first global-memory access (the wait returns once the
+// previous grid has completed and its writes are visible).  pdl_launch_dependents() lets the NEXT kernel start early.
+// Both are no-ops in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace lsk

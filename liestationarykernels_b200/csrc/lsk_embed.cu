@@ -104,9 +104,10 @@ __host__ __device__ constexpr int even_mask(int k) {          // even-parity 5-b
 template <int J, int I>
 __device__ __forceinline__ void rotor_step(double (&m)[5][5], double (&R)[16]) {
     const double a = m[J][J], b = m[I][J];
-    const double r = hypot(a, b);
-    if (r == 0.0) return;
-    const double c = a / r, s = b / r;
+    const double r2 = fma(a, a, b * b);              // entries of an orthogonal matrix: no over/underflow to guard
+    if (r2 == 0.0) return;
+    const double ir = rsqrt(r2);                     // the latency chain of this kernel is 10 of these steps: two rsqrt
+    const double c = a * ir, s = b * ir;             // per step instead of hypot + sqrt + three divisions
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const double rj = m[J][k], ri = m[I][k];
@@ -114,8 +115,8 @@ __device__ __forceinline__ void rotor_step(double (&m)[5][5], double (&R)[16]) {
         m[I][k] = -s * rj + c * ri;
     }
     double ch, sh;                       // half-angle, formed without cancellation
-    if (c >= 0.0) { ch = sqrt(0.5 * (1.0 + c)); sh = s / (2.0 * ch); }
-    else { sh = (s >= 0.0 ? 1.0 : -1.0) * sqrt(0.5 * (1.0 - c)); ch = s / (2.0 * sh); }
+    if (c >= 0.0) { const double h = 0.5 * (1.0 + c), t = rsqrt(h); ch = h * t; sh = 0.5 * s * t; }
+    else { const double h = 0.5 * (1.0 - c), t = rsqrt(h); sh = (s >= 0.0 ? h : -h) * t; ch = 0.5 * fabs(s) * t; }
     constexpr int B = (1 << J) | (1 << I);
     double nw[16];
 #pragma unroll
@@ -149,9 +150,25 @@ __device__ __forceinline__ void spin5_rotor(const double* __restrict__ x, double
     rotor_step<3, 4>(m, R);
 }
 
+// One operand of an embedding launch.  A launch carries one or two of them (blockIdx.y): kernel(x, y) embeds both
+// sides with a single launch, which matters once the row-sharded pair kernel is down to a few hundred microseconds.
+struct EmbedJob {
+    const double* x;
+    long long num;
+    double* out;
+    EmbedSpec spec;
+};
+
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
-embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, EmbedSpec spec, double* __restrict__ out) {
+embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ EmbedJob job1, int n, int kg_total) {
+    pdl_launch_dependents();
+    const EmbedJob& job = blockIdx.y ? job1 : job0;
+    const double* __restrict__ x = job.x;
+    double* __restrict__ out = job.out;
+    const long long num = job.num;
+    const EmbedSpec& spec = job.spec;
+    pdl_wait();                                   // x may come from the kernel launched just before (e.g. space.rand)
     const long long total = ((num + ROW_PAD - 1) / ROW_PAD) * (ROW_PAD / PANEL) * (long long)kg_total * (PANEL * 4);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx & 3);
@@ -204,8 +221,14 @@ embed_kernel(const double* __restrict__ x, long long num, int n, int kg_total, E
 // WITH_MATRIX the same thread also writes the matrix itself (25 values + 3 zeros) into k-groups [gm, gm + 7), which
 // makes this kernel the whole SO(5) embedding (one launch per operand)
 template <bool WITH_MATRIX>
-__global__ void __launch_bounds__(128)
-spin5_embed_kernel(const double* __restrict__ x, long long num, int kg_total, int g0, int gm, double* __restrict__ out) {
+__global__ void __launch_bounds__(64)
+spin5_embed_kernel(const double* __restrict__ x0, long long num0, double* __restrict__ out0,
+                   const double* __restrict__ x1, long long num1, double* __restrict__ out1, int kg_total, int g0, int gm) {
+    pdl_launch_dependents();
+    const double* __restrict__ x = blockIdx.y ? x1 : x0;
+    double* __restrict__ out = blockIdx.y ? out1 : out0;
+    const long long num = blockIdx.y ? num1 : num0;
+    pdl_wait();
     const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_padded) return;
@@ -235,14 +258,12 @@ spin5_embed_kernel(const double* __restrict__ x, long long num, int kg_total, in
 
 }  // namespace lsk
 
-extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_complex, int nseg,
-                                const int* wedge, const int* part, const int* group_begin, int kg_total,
-                                void* out, void* stream) {
-    using namespace lsk;
-    if (!x || !out || !wedge || !part || !group_begin) return LSK_EARG;
+namespace lsk {
+
+static int make_spec(long long num, int n, int is_complex, int nseg, const int* wedge, const int* part, const int* group_begin,
+                     int kg_total, EmbedSpec& spec) {
+    if (!wedge || !part || !group_begin) return LSK_EARG;
     if (num < 0 || n < 1 || n > 8 || nseg < 1 || nseg > 4 || kg_total < 1) return LSK_ESIZE;
-    if (num == 0) return 0;
-    EmbedSpec spec;
     spec.nseg = nseg;
     for (int s = 0; s < 4; ++s) { spec.wedge[s] = 1; spec.part[s] = 0; spec.group_begin[s] = 0; spec.length[s] = 0; }
     for (int s = 0; s < nseg; ++s) {
@@ -263,28 +284,81 @@ extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_comp
         if (group_begin[s] < 0 || end > kg_total) return LSK_ESIZE;
         if (s > 0 && group_begin[s] < spec.group_begin[s - 1] + (spec.length[s - 1] + 3) / 4) return LSK_EARG;
     }
-    const long long total = ((num + ROW_PAD - 1) / ROW_PAD) * (ROW_PAD / PANEL) * (long long)kg_total * (PANEL * 4);
-    long long blocks = (total + 255) / 256;
+    return 0;
+}
+
+static bool is_so5_standard(const EmbedSpec& spec, int n, int is_complex, int kg_total) {
+    return !is_complex && n == 5 && spec.nseg == 2 && spec.wedge[0] == 1 && spec.wedge[1] == LSK_SEG_SPIN5 &&
+           spec.group_begin[0] == 0 && spec.group_begin[1] == 7 && kg_total == 11;
+}
+
+// embeds one or two operands (njobs) that share n, is_complex and kg_total with ONE launch where the layout allows it
+static int embed_jobs(EmbedJob* jobs, int njobs, int n, int is_complex, int kg_total, cudaStream_t st) {
+    long long rows_max = 0, total_max = 0;
+    for (int j = 0; j < njobs; ++j) {
+        const long long rp = ((jobs[j].num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
+        rows_max = rp > rows_max ? rp : rows_max;
+        const long long total = rp / PANEL * (long long)kg_total * (PANEL * 4);
+        total_max = total > total_max ? total : total_max;
+    }
+    if (rows_max == 0) return 0;
+    const EmbedJob& j0 = jobs[0];
+    const EmbedJob& j1 = jobs[njobs - 1];
+    bool all_so5 = true;
+    for (int j = 0; j < njobs; ++j) all_so5 = all_so5 && is_so5_standard(jobs[j].spec, n, is_complex, kg_total);
+    if (all_so5) {
+        // the standard SO(5) layout [matrix | rotor]: one thread per point writes both segments
+        cudaError_t e = launch_pdl(spin5_embed_kernel<true>, dim3((unsigned)((rows_max + 63) / 64), njobs), dim3(64), 0, st,
+                                   j0.x, j0.num, j0.out, j1.x, j1.num, j1.out, kg_total, 7, 0);
+        return (int)e;
+    }
+    long long blocks = (total_max + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (!is_complex && n == 5 && nseg == 2 && spec.wedge[0] == 1 && spec.wedge[1] == LSK_SEG_SPIN5 &&
-        spec.group_begin[0] == 0 && spec.group_begin[1] == 7 && kg_total == 11) {
-        // the standard SO(5) layout [matrix | rotor]: one fused launch
-        const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
-        spin5_embed_kernel<true><<<(unsigned)((rows_padded + 127) / 128), 128, 0, st>>>(
-            static_cast<const double*>(x), num, kg_total, 7, 0, static_cast<double*>(out));
-        return (int)cudaGetLastError();
-    }
-    if (is_complex) embed_kernel<true><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
-    else embed_kernel<false><<<(int)blocks, 256, 0, st>>>(static_cast<const double*>(x), num, n, kg_total, spec, static_cast<double*>(out));
-    for (int s = 0; s < nseg; ++s) {
-        if (spec.wedge[s] == LSK_SEG_SPIN5) {
-            const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
-            spin5_embed_kernel<false><<<(unsigned)((rows_padded + 127) / 128), 128, 0, st>>>(
-                static_cast<const double*>(x), num, kg_total, spec.group_begin[s], 0, static_cast<double*>(out));
-        }
-    }
+    cudaError_t e;
+    if (is_complex) e = launch_pdl(embed_kernel<true>, dim3((unsigned)blocks, njobs), dim3(256), 0, st, j0, j1, n, kg_total);
+    else e = launch_pdl(embed_kernel<false>, dim3((unsigned)blocks, njobs), dim3(256), 0, st, j0, j1, n, kg_total);
+    if (e != cudaSuccess) return (int)e;
+    for (int j = 0; j < njobs; ++j)
+        for (int s = 0; s < jobs[j].spec.nseg; ++s)
+            if (jobs[j].spec.wedge[s] == LSK_SEG_SPIN5 && jobs[j].num > 0) {
+                const long long rp = ((jobs[j].num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
+                e = launch_pdl(spin5_embed_kernel<false>, dim3((unsigned)((rp + 63) / 64), 1), dim3(64), 0, st,
+                               jobs[j].x, jobs[j].num, jobs[j].out, jobs[j].x, jobs[j].num, jobs[j].out,
+                               kg_total, jobs[j].spec.group_begin[s], 0);
+                if (e != cudaSuccess) return (int)e;
+            }
     return (int)cudaGetLastError();
+}
+
+}  // namespace lsk
+
+extern "C" int lsk_embed_points(const void* x, long long num, int n, int is_complex, int nseg,
+                                const int* wedge, const int* part, const int* group_begin, int kg_total,
+                                void* out, void* stream) {
+    using namespace lsk;
+    if (!x || !out) return LSK_EARG;
+    EmbedJob job;
+    const int rc = make_spec(num, n, is_complex, nseg, wedge, part, group_begin, kg_total, job.spec);
+    if (rc) return rc;
+    if (num == 0) return 0;
+    job.x = static_cast<const double*>(x); job.num = num; job.out = static_cast<double*>(out);
+    return embed_jobs(&job, 1, n, is_complex, kg_total, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lsk_embed_points2(const void* x, long long num_x, const int* part_x, void* out_x,
+                                 const void* y, long long num_y, const int* part_y, void* out_y,
+                                 int n, int is_complex, int nseg, const int* wedge, const int* group_begin, int kg_total,
+                                 void* stream) {
+    using namespace lsk;
+    if (!x || !y || !out_x || !out_y) return LSK_EARG;
+    EmbedJob jobs[2];
+    int rc = make_spec(num_x, n, is_complex, nseg, wedge, part_x, group_begin, kg_total, jobs[0].spec);
+    if (rc) return rc;
+    rc = make_spec(num_y, n, is_complex, nseg, wedge, part_y, group_begin, kg_total, jobs[1].spec);
+    if (rc) return rc;
+    jobs[0].x = static_cast<const double*>(x); jobs[0].num = num_x; jobs[0].out = static_cast<double*>(out_x);
+    jobs[1].x = static_cast<const double*>(y); jobs[1].num = num_y; jobs[1].out = static_cast<double*>(out_y);
+    return embed_jobs(jobs, 2, n, is_complex, kg_total, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lsk_version(void) { return LSK_VERSION; }

@@ -44,6 +44,29 @@ def embed(plan: GroupPlan, x: torch.Tensor, side: str) -> torch.Tensor:
     return out
 
 
+def embed_pair(plan: GroupPlan, x: torch.Tensor, y: torch.Tensor):
+    """Embeddings of both operands of `kernel(x, y)` with ONE launch (side A for x, side B for y)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    x = _as_matrix_batch(x, plan.n, plan.is_complex)
+    y = _as_matrix_batch(y, plan.n, plan.is_complex)
+    if x.shape[0] == 0 or y.shape[0] == 0 or [s[0] for s in plan.segments_a] != [s[0] for s in plan.segments_b]:
+        return embed(plan, x, "a"), embed(plan, y, "b")
+    nseg = len(plan.segments_a)
+    wedge = (ctypes.c_int * nseg)(*[s[0] for s in plan.segments_a])
+    part_a = (ctypes.c_int * nseg)(*[s[1] for s in plan.segments_a])
+    part_b = (ctypes.c_int * nseg)(*[s[1] for s in plan.segments_b])
+    begin = (ctypes.c_int * nseg)(*plan.group_begin)
+    ea = torch.empty(lib.lsk_embed_buffer_doubles(x.shape[0], plan.kg_total), dtype=F64, device=x.device)
+    eb = torch.empty(lib.lsk_embed_buffer_doubles(y.shape[0], plan.kg_total), dtype=F64, device=x.device)
+    xr, yr = (torch.view_as_real(x), torch.view_as_real(y)) if plan.is_complex else (x, y)
+    _lib.check(lib.lsk_embed_points2(_lib.ptr(xr), x.shape[0], part_a, _lib.ptr(ea), _lib.ptr(yr), y.shape[0], part_b,
+                                     _lib.ptr(eb), plan.n, int(plan.is_complex), nseg, wedge, begin, plan.kg_total,
+                                     _lib.stream_ptr()), "lsk_embed_points2")
+    _lib.count_launch()
+    return ea, eb
+
+
 def pairwise_poly(emb_a: torch.Tensor, emb_b: torch.Tensor, n_rows: int, n_cols: int, kg_total: int,
                   epilogue: _lib.LskEpilogue, out: torch.Tensor | None = None, symmetric: bool = False) -> torch.Tensor:
     """out[i, j] = scale * P(invariants of pair (i, j)) — the fused covariance tile kernel.

@@ -100,9 +100,11 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
             return _WeightedCharacterSum.apply(self, x, y, normalize, out, *params)
         plan = manifold.plan
         ep = self._epilogue(normalize)
-        ea = ops.embed(plan, x, "a")
         same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides
-        eb = ea if same else ops.embed(plan, y, "b")
+        if same:
+            ea = eb = ops.embed(plan, x, "a")
+        else:
+            ea, eb = ops.embed_pair(plan, x, y)                    # one launch for both operands
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 
     # ---- differentiable path ---------------------------------------------------------------------------------
@@ -130,9 +132,11 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         manifold = self.manifold
         plan = manifold.plan
         ep = plan.epilogue(np.asarray(coefs, dtype=np.float64) * manifold._dims, 1.0, form=self.form)
-        ea = ops.embed(plan, x, "a")
         same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides
-        eb = ea if same else ops.embed(plan, y, "b")
+        if same:
+            ea = eb = ops.embed(plan, x, "a")
+        else:
+            ea, eb = ops.embed_pair(plan, x, y)                    # one launch for both operands
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 
 
