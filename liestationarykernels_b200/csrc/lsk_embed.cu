@@ -100,37 +100,59 @@ __host__ __device__ constexpr int even_mask(int k) {          // even-parity 5-b
     return (k << 1) | (c & 1);
 }
 
+template <int J, int I>
+struct RotorTable {
+    int dst[16];
+    bool neg[16];
+    constexpr RotorTable() : dst{}, neg{} {
+        const int B = (1 << J) | (1 << I);
+        for (int k = 0; k < 16; ++k) {
+            const int A = even_mask(k);
+            dst[k] = (A ^ B) >> 1;
+            neg[k] = blade_sign(A, B) < 0.0;
+        }
+    }
+};
+
+// 1 / sqrt(x) for normal positive x: hardware seed (2^-22) + one third-order Newton step, no special-case paths
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    y = fma(y * e, fma(0.375, e, 0.5), y);
+    const double e2 = fma(-x * y, y, 1.0);           // second (linear) step: the seed error cubed is ~2^-60, this
+    return fma(0.5 * y, e2, y);                      // step removes what the rounding of the first one left
+}
+
 // R <- R * (ch - sh e_J e_I): all blade indices and signs are compile-time constants, everything stays in registers
 template <int J, int I>
 __device__ __forceinline__ void rotor_step(double (&m)[5][5], double (&R)[16]) {
+    // Branch-free: this kernel is one long dependent instruction chain per point (latency-bound, a few warps per SM), so
+    // every avoided branch, special-case path and division shortens the launch that precedes each pair kernel.
     const double a = m[J][J], b = m[I][J];
-    const double r2 = fma(a, a, b * b);              // entries of an orthogonal matrix: no over/underflow to guard
-    if (r2 == 0.0) return;
-    const double ir = rsqrt(r2);                     // the latency chain of this kernel is 10 of these steps: two rsqrt
-    const double c = a * ir, s = b * ir;             // per step instead of hypot + sqrt + three divisions
+    const double r2 = fma(a, a, b * b);              // entries of an orthogonal matrix: no overflow to guard
+    const bool live = r2 > 1e-280;                   // column already aligned (a = b = 0): identity step
+    const double ir = rsqrt_pos(live ? r2 : 1.0);
+    const double c = live ? a * ir : 1.0, s = live ? b * ir : 0.0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const double rj = m[J][k], ri = m[I][k];
-        m[J][k] = c * rj + s * ri;
-        m[I][k] = -s * rj + c * ri;
+        m[J][k] = fma(c, rj, s * ri);
+        m[I][k] = fma(c, ri, -s * rj);
     }
-    double ch, sh;                       // half-angle, formed without cancellation
-    if (c >= 0.0) { const double h = 0.5 * (1.0 + c), t = rsqrt(h); ch = h * t; sh = 0.5 * s * t; }
-    else { const double h = 0.5 * (1.0 - c), t = rsqrt(h); sh = (s >= 0.0 ? h : -h) * t; ch = 0.5 * fabs(s) * t; }
-    constexpr int B = (1 << J) | (1 << I);
+    // half-angle without cancellation: h = (1 + |c|) / 2 in [1/2, 1];  c >= 0: (ch, sh) = (sqrt h, s / (2 sqrt h)),
+    // c < 0: (|s| / (2 sqrt h), sign(s) sqrt h)
+    const double h = 0.5 * (1.0 + fabs(c)), t = rsqrt_pos(h);
+    const double big = h * t, small = 0.5 * t;
+    const double ch = (c >= 0.0) ? big : fabs(s) * small;
+    const double sh = (c >= 0.0) ? s * small : copysign(big, s);
+    // target blade (A ^ B) >> 1 receives -sh * sign(A, B) * R[k]; destinations and signs are compile-time tables
+    constexpr RotorTable<J, I> tab{};
     double nw[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        // target blade k receives ch * R[k] and -sh * sign * R[src] with src = k ^ (B >> 1) adjusted for parity
-        constexpr int dummy = 0; (void)dummy;
-        nw[k] = ch * R[k];
-    }
+    for (int k = 0; k < 16; ++k) nw[k] = ch * R[k];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int A = even_mask(k);
-        const int dst = (A ^ B) >> 1;
-        nw[dst] = fma(-sh * blade_sign(A, B), R[k], nw[dst]);
-    }
+    for (int k = 0; k < 16; ++k) nw[tab.dst[k]] = fma(tab.neg[k] ? sh : -sh, R[k], nw[tab.dst[k]]);
 #pragma unroll
     for (int k = 0; k < 16; ++k) R[k] = nw[k];
 }
