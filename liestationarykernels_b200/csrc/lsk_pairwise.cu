@@ -20,6 +20,10 @@
 
 namespace lsk {
 
+// lsk_pairwise_so5.cu: LSK_EUNSUPPORTED when the problem is not one of the compiled SO(5) shapes
+int so5_stair_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
+                     const LskEpilogue& p, int sms, cudaStream_t stream);
+
 constexpr int PANEL_STAGE = KG_PER_STAGE * PANEL * 4;            // one panel, one stage: 2048 doubles = 16 KB
 constexpr int A_STAGE = (BM / PANEL) * PANEL_STAGE;              // two A panels
 constexpr int B_STAGE = PANEL_STAGE;
@@ -81,48 +85,6 @@ __device__ __forceinline__ void epi_stair2(const LskEpilogue& p, const double (&
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) outer[r] = fma(outer[r], s2[r], inner[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) out[r] = outer[r];
-}
-
-// Shape-specialised staircase: the row lengths are template constants (bits [4k, 4k+4) of SHAPE = coefficient pairs of
-// row slot k as in LskEpilogue::stair_shape, bit 48 + k = the slot's first coefficient is padding, i.e. the row has an odd
-// number of coefficients), so the nested Horner scheme is straight-line code whose coefficients are immediate-offset
-// constant-bank operands of the DFMAs themselves: no coefficient loads, no loop control, one DFMA per coefficient.
-template <int R, unsigned long long SHAPE>
-__device__ __forceinline__ void epi_stair2_fixed(const LskEpilogue& p, const double (&s1)[R], const double (&s2)[R], double (&out)[R]) {
-    double outer[R];
-    const int once = p.nvars - 1;
-#pragma unroll
-    for (int k = 0; k < LSK_STAIR_MAX_ROWS; ++k) {
-        const int pairs = (int)((SHAPE >> (4 * k)) & 15ull);
-        const int odd = (int)((SHAPE >> (48 + k)) & 1ull);
-        const int len = 2 * pairs - odd, base = LSK_STAIR_STRIDE * k + odd;
-        if (pairs > 0) {
-            // Each row is the body of a loop that runs exactly once (`once` = nvars - 1 = 1 is a run-time value): the
-            // back edge keeps ptxas from interleaving the independent rows, which costs registers (spills at 128) and
-            // buys nothing - 8 entries x 2 issue cycles already cover the 8-cycle DFMA latency.
-            int it = 0;
-#pragma unroll 1
-            do {
-                double inner[R];
-                if (len == 1) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) inner[r] = p.coef[base];
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) inner[r] = fma(s1[r], p.coef[base], p.coef[base + 1]);
-#pragma unroll
-                    for (int q = 2; q < len; ++q) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) inner[r] = fma(inner[r], s1[r], p.coef[base + q]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) outer[r] = (k == 0) ? inner[r] : fma(outer[r], s2[r], inner[r]);
-            } while (++it < once);
         }
     }
 #pragma unroll
@@ -202,7 +164,7 @@ __device__ __forceinline__ int chunk_len(int remaining) {
 // main kernel
 //   EPI: epilogue kind;  NF: number of bilinear forms;  NV: number of variables (SPARSE only);  D: ORBIT2 size
 // ------------------------------------------------------------------------------------------------------------
-template <int EPI, int NF, int NV, int D, bool SYM, unsigned long long SHAPE>
+template <int EPI, int NF, int NV, int D, bool SYM>
 __global__ void __launch_bounds__(THREADS, 1)
 pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 int n_rows, int n_cols, int kg_total,               // kg_total: k-groups per row of A and B
@@ -401,43 +363,6 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 }
             }
         };
-        if constexpr (EPI == LSK_EPI_STAIR2 && SHAPE != 0ull) {
-            // shape-specialised path: ONE copy of the straight-line polynomial, executed for both halves of the warp tile
-            // (the second half of the accumulators is shifted into the registers of the first after use)
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                constexpr int R = 8;
-                produce_ahead();
-                double var[2][R], res[R];
-#pragma unroll
-                for (int e = 0; e < R; ++e) {
-                    const int ml = e >> 2, n = (e >> 1) & 1, i = e & 1;
-#pragma unroll
-                    for (int v = 0; v < 2; ++v) {
-                        double x = p.aff[v][0];
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) {
-                            const double u = acc[f][ml][n][i];
-                            const double w = ((p.reserved >> (8 + f)) & 1) ? u * u : u;
-                            x = fma(p.aff[v][1 + f], w, x);
-                        }
-                        var[v][e] = x;
-                    }
-                }
-                epi_stair2_fixed<R, SHAPE>(p, var[0], var[1], res);
-#pragma unroll
-                for (int e = 0; e < R; e += 2) {
-                    const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
-                    store_pair(row0 + m * 8, col0 + n * 8, 0, p.scale * res[e], p.scale * res[e + 1]);
-                }
-#pragma unroll
-                for (int f = 0; f < NF; ++f)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m)
-#pragma unroll
-                        for (int n = 0; n < 2; ++n) { acc[f][m][n][0] = acc[f][m + 2][n][0]; acc[f][m][n][1] = acc[f][m + 2][n][1]; }
-            }
-        } else
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             constexpr int R = 8;
@@ -504,10 +429,10 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     }
 }
 
-template <int EPI, int NF, int NV, int D, bool SYM = false, unsigned long long SHAPE = 0ull>
+template <int EPI, int NF, int NV, int D, bool SYM = false>
 static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                   const LskEpilogue& p, int max_ctas, cudaStream_t stream) {
-    auto kern = pairwise_kernel<EPI, NF, NV, D, SYM, SHAPE>;
+    auto kern = pairwise_kernel<EPI, NF, NV, D, SYM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const long long rt = (n_rows + BM - 1) / BM, cp = (n_cols + BN - 1) / BN;
@@ -568,14 +493,9 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
             if (k < p.nterms ? (pairs < 1 || 2 * pairs > LSK_STAIR_STRIDE || p.row_len[k] != 2 * pairs) : pairs != 0) return LSK_EARG;
         }
         if (p.nforms == 2) {
-            // shape-specialised instantiations (straight-line polynomial): the SO(5) tables of the common truncations
-#define LSK_GO_SHAPE(S) if (p.stair_shape == (S)) { \
-                if (want_sym) return launch<LSK_EPI_STAIR2, 2, 2, 1, true, (S)>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st); \
-                return launch<LSK_EPI_STAIR2, 2, 2, 1, false, (S)>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st); }
-            LSK_GO_SHAPE(0x54e087766544321ull)      // SO(5), first 100 irreps
-            LSK_GO_SHAPE(0x1b000000043221ull)       // SO(5), first 20 irreps (default order)
-            LSK_GO_SHAPE(0x6000000000321ull)        // SO(5), first 10 irreps
-#undef LSK_GO_SHAPE
+            // the SO(5) tables of the common truncations have a dedicated kernel (lsk_pairwise_so5.cu)
+            const int rc = so5_stair_launch(a, b, nr, nc, kg_total, o, ld_out, p, sms, st);
+            if (rc != LSK_EUNSUPPORTED) return rc;
             LSK_GO_SYM(LSK_EPI_STAIR2, 2, 2, 1);
         }
         return LSK_EUNSUPPORTED;
