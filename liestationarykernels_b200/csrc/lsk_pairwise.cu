@@ -164,7 +164,9 @@ __device__ __forceinline__ int chunk_len(int remaining) {
 // main kernel
 //   EPI: epilogue kind;  NF: number of bilinear forms;  NV: number of variables (SPARSE only);  D: ORBIT2 size
 // ------------------------------------------------------------------------------------------------------------
-template <int EPI, int NF, int NV, int D, bool SYM>
+//   MT:  8-row accumulator fragments per warp (4: 128 x 64 tile, two A panels;  2: 64 x 64 tile, one A panel - for
+//        problems with three or four bilinear forms, whose accumulators would not fit in registers otherwise)
+template <int EPI, int NF, int NV, int D, bool SYM, int MT>
 __global__ void __launch_bounds__(THREADS, 1)
 pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 int n_rows, int n_cols, int kg_total,               // kg_total: k-groups per row of A and B
@@ -177,7 +179,9 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
     uint64_t* empty_bar = full_bar + STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row_tiles = (n_rows + BM - 1) / BM, col_panels = (n_cols + BN - 1) / BN;
+    constexpr int BMT = 32 * MT;                    // rows per CTA tile
+    static_assert(MT == 4 || (MT == 2 && !SYM), "the triangular schedule assumes 128 x 64 tiles");
+    const int row_tiles = (n_rows + BMT - 1) / BMT, col_panels = (n_cols + BN - 1) / BN;
     // symmetric mode (bit 1 of `reserved`; A and B describe the same points): only tiles that reach the diagonal or lie
     // above it are computed, every entry above the diagonal is also stored at its mirror position
     constexpr bool sym = SYM;        // compile-time: the general kernel carries none of the triangular-schedule code
@@ -222,14 +226,14 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         if (!free_slot) return false;
         int pr, pc;
         tile_coords(p_tile, pr, pc);
-        const double* srcA0 = A + ((size_t)(2 * pr) * kg_total + p_group) * (PANEL * 4);   // operands are padded to
-        const double* srcA1 = srcA0 + (size_t)kg_total * (PANEL * 4);                       // ROW_PAD rows: both exist
+        const double* srcA0 = A + ((size_t)((MT / 2) * pr) * kg_total + p_group) * (PANEL * 4);   // operands are padded to
+        const double* srcA1 = srcA0 + (size_t)kg_total * (PANEL * 4);                              // ROW_PAD rows: both exist
         const double* srcB = B + ((size_t)pc * kg_total + p_group) * (PANEL * 4);
         const int ng = chunk_len(p.group_end[p_form] - p_group);
         const uint32_t bytes = (uint32_t)ng * PANEL * 4 * 8;
-        mbar_expect_tx(&full_bar[p_stage], 3 * bytes);
+        mbar_expect_tx(&full_bar[p_stage], (MT / 2 + 1) * bytes);
         bulk_g2s(sA + p_stage * A_STAGE, srcA0, bytes, &full_bar[p_stage]);
-        bulk_g2s(sA + p_stage * A_STAGE + PANEL_STAGE, srcA1, bytes, &full_bar[p_stage]);
+        if constexpr (MT == 4) bulk_g2s(sA + p_stage * A_STAGE + PANEL_STAGE, srcA1, bytes, &full_bar[p_stage]);
         bulk_g2s(sB + p_stage * B_STAGE, srcB, bytes, &full_bar[p_stage]);
         p_group += ng;
         if (p_group >= p.group_end[p_form]) {
@@ -266,7 +270,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     // ===================== consumer warps: 4 (rows) x 4 (cols), warp tile 32 x 16 =====================
     const int wr = warp >> 2, wc = warp & 3;
     const int frag = (lane >> 2) * 4 + (lane & 3);           // offset of this lane inside an 8x4 fragment
-    const int a_off = (wr >> 1) * PANEL_STAGE + ((wr & 1) * 32) * 4 + frag;
+    const int a_off = MT == 4 ? (wr >> 1) * PANEL_STAGE + ((wr & 1) * 32) * 4 + frag : (wr * 16) * 4 + frag;
     const int b_off = (wc * 16) * 4 + frag;
     const bool vec_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
@@ -275,11 +279,11 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         int pr, pc;
         tile_coords(t, pr, pc);
-        double acc[NF][4][2][2];
+        double acc[NF][MT][2][2];
 #pragma unroll
         for (int f = 0; f < NF; ++f)
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
+            for (int m = 0; m < MT; ++m)
 #pragma unroll
                 for (int n = 0; n < 2; ++n) { acc[f][m][n][0] = 0.0; acc[f][m][n][1] = 0.0; }
 
@@ -298,13 +302,13 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 if (ng == KG_PER_STAGE) {
 #pragma unroll
                     for (int gi = 0; gi < KG_PER_STAGE; ++gi) {
-                        double a[4], b[2];
+                        double a[MT], b[2];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) a[m] = pa[gi * (PANEL * 4) + m * 32];
+                        for (int m = 0; m < MT; ++m) a[m] = pa[gi * (PANEL * 4) + m * 32];
 #pragma unroll
                         for (int n = 0; n < 2; ++n) b[n] = pb[gi * (PANEL * 4) + n * 32];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m)
+                        for (int m = 0; m < MT; ++m)
 #pragma unroll
                             for (int n = 0; n < 2; ++n) dmma884(acc[f][m][n], a[m], b[n]);
                     }
@@ -312,13 +316,13 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 #pragma unroll
                     for (int gi = 0; gi < KG_PER_STAGE - 1; ++gi) {
                         if (gi < ng) {
-                            double a[4], b[2];
+                            double a[MT], b[2];
 #pragma unroll
-                            for (int m = 0; m < 4; ++m) a[m] = pa[gi * (PANEL * 4) + m * 32];
+                            for (int m = 0; m < MT; ++m) a[m] = pa[gi * (PANEL * 4) + m * 32];
 #pragma unroll
                             for (int n = 0; n < 2; ++n) b[n] = pb[gi * (PANEL * 4) + n * 32];
 #pragma unroll
-                            for (int m = 0; m < 4; ++m)
+                            for (int m = 0; m < MT; ++m)
 #pragma unroll
                                 for (int n = 0; n < 2; ++n) dmma884(acc[f][m][n], a[m], b[n]);
                         }
@@ -332,7 +336,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         }
 
         // ---- class polynomial on the accumulator fragments, 8 entries at a time ----
-        const int row0 = pr * BM + wr * 32 + (lane >> 2);
+        const int row0 = pr * BMT + wr * (8 * MT) + (lane >> 2);
         const int col0 = pc * BN + wc * 16 + 2 * (lane & 3);
         // writes the pair (r0, r1) at (row, col + col_shift), (row, col + col_shift + 1); `col` is even
         auto store_pair = [&](int row, int col, long long col_shift, double r0, double r1) {
@@ -364,7 +368,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             }
         };
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < MT / 2; ++h) {
             constexpr int R = 8;
             produce_ahead();
             double var[NV][R], res[R];
@@ -429,13 +433,13 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     }
 }
 
-template <int EPI, int NF, int NV, int D, bool SYM = false>
+template <int EPI, int NF, int NV, int D, bool SYM = false, int MT = 4>
 static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                   const LskEpilogue& p, int max_ctas, cudaStream_t stream) {
-    auto kern = pairwise_kernel<EPI, NF, NV, D, SYM>;
+    auto kern = pairwise_kernel<EPI, NF, NV, D, SYM, MT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    const long long rt = (n_rows + BM - 1) / BM, cp = (n_cols + BN - 1) / BN;
+    const long long rt = (n_rows + 32 * MT - 1) / (32 * MT), cp = (n_cols + BN - 1) / BN;
     const long long tiles = SYM ? rt * cp - rt * (rt - 1) : rt * cp;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, SMEM_BYTES);
@@ -477,7 +481,7 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
     double* o = static_cast<double*>(out);
     const int nr = (int)n_rows, nc = (int)n_cols;
 
-#define LSK_GO(EPI, NF, NV, D) return launch<EPI, NF, NV, D>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st)
+#define LSK_GO(EPI, NF, NV, D) return launch<EPI, NF, NV, D, false, ((NF) >= 3 ? 2 : 4)>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st)
 #define LSK_GO_SYM(EPI, NF, NV, D) do { if (want_sym) return launch<EPI, NF, NV, D, true>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st); \
                                         return launch<EPI, NF, NV, D, false>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st); } while (0)
     const bool want_sym = ((p.reserved >> 1) & 1) != 0;
