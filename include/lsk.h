@@ -34,10 +34,15 @@ extern "C" {
 #define LSK_EPI_CHEB1       1   /* rank 1: sum_k coef[k] T_k(var0)  (Clenshaw)                                   */
 #define LSK_EPI_STAIR2      2   /* rank 2: sum_b var1^b sum_a C[b][a] var0^a  (nested Horner, fast form)         */
 #define LSK_EPI_ORBIT2      3   /* rank 2: sum_ab W[a][b] T_a(c1) T_b(c2), c1+c2 = var0, c1 c2 = var1 (robust)   */
-#define LSK_EPI_SPARSE      4   /* any  : sum_t coef[2t] prod_v var_v^e_tv, e packed 8 bits each in coef[2t+1]  */
+#define LSK_EPI_SPARSE      4   /* any  : sum_t coef[2t] prod_v var_v^e_tv, e packed 8 bits each in coef[2t+1]
+                                   (monomial list; read by lsk_homog_pairs only)                                  */
 #define LSK_EPI_LINEAR      5   /* out = scale * form_0  (Gram of two feature maps)                              */
 #define LSK_EPI_FEAT_CHEB1  6   /* per-irrep rows, rank 1 (row l: row_len[l] Chebyshev coefficients)             */
-#define LSK_EPI_FEAT_SPARSE 7   /* per-irrep rows, any rank (row l: row_len[l] sparse terms)                     */
+#define LSK_EPI_FEAT_SPARSE 7   /* per-irrep rows, any rank (row l: row_len[l] sparse terms; lsk_homog_pairs)    */
+#define LSK_EPI_HORNER      8   /* any  : nested Horner tape, nterms steps (coef[2t], op = low word of coef[2t+1]):
+                                   op 0: a0 = a0 v0 + c;  1: a0 = c;  2+3(l-1): al = al vl + a(l-1);  +1: al = a(l-1);
+                                   +2: al = al vl;  result a(nvars-1)  (SU(3..5), SO(4), SO(6), SO(7))               */
+#define LSK_EPI_FEAT_HORNER 9   /* per-irrep rows, any rank: row l is a tape of row_len[l] steps                  */
 
 /* output layouts */
 #define LSK_OUT_ROW_MAJOR   0   /* out[i * ld_out + j]                                                            */
@@ -51,7 +56,7 @@ typedef struct LskEpilogue {
     int32_t kind;
     int32_t nforms;
     int32_t nvars;
-    int32_t nterms;                      /* CHEB1 #coef; STAIR2 #rows; ORBIT2 matrix size; SPARSE #terms; FEAT_* #irreps */
+    int32_t nterms;                      /* CHEB1 #coef; STAIR2 #rows; ORBIT2 matrix size; SPARSE #terms; HORNER #steps; FEAT_* #irreps */
     int32_t group_begin[LSK_MAX_FORMS];
     int32_t group_end[LSK_MAX_FORMS];
     int32_t row_len[LSK_MAX_ROWS];

@@ -19,6 +19,7 @@ MAX_COEF = 400
 MAX_ROWS = 24
 
 EPI_CHEB1, EPI_STAIR2, EPI_ORBIT2, EPI_SPARSE, EPI_LINEAR, EPI_FEAT_CHEB1, EPI_FEAT_SPARSE = 1, 2, 3, 4, 5, 6, 7
+EPI_HORNER, EPI_FEAT_HORNER = 8, 9
 OUT_ROW_MAJOR, OUT_PANEL_MAJOR, FEAT_COMPLEX = 0, 1, 2
 
 

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import characters as ch
 from . import invariants as inv
-from ._lib import (EPI_CHEB1, EPI_ORBIT2, EPI_SPARSE, EPI_STAIR2, MAX_COEF, MAX_FORMS, MAX_ROWS, MAX_VARS,
+from ._lib import (EPI_CHEB1, EPI_HORNER, EPI_ORBIT2, EPI_SPARSE, EPI_STAIR2, MAX_COEF, MAX_FORMS, MAX_ROWS, MAX_VARS,
                    LskEpilogue)
 
 
@@ -277,25 +277,24 @@ class GroupPlan:
                 for b in range(Dp):
                     ep.coef[a * Dp + b] = full[a, b]
             return ep
-        # sparse
+        # sparse polynomial in nvars variables: nested-Horner tape (csrc/lsk_pairwise.cu `epi_tape`)
         coef = _dot_long(w, self.M)
-        keep = [(c, e) for c, e in zip(coef, self.sparse_expo) if c != 0.0]
-        if 2 * len(keep) > MAX_COEF:
-            raise ValueError("too many polynomial terms for the sparse epilogue (%d > %d)" % (len(keep), MAX_COEF // 2))
-        ep.kind, ep.nterms = EPI_SPARSE, len(keep)
-        for t, (c, e) in enumerate(keep):
-            ep.coef[2 * t] = c
-            packed = 0
-            for i, ei in enumerate(e):
-                assert 0 <= ei < 256
-                packed |= int(ei) << (8 * i)
-            ep.coef[2 * t + 1] = np.array([packed], dtype=np.uint64).view(np.float64)[0]
+        terms = {tuple(e): float(c) for c, e in zip(coef, self.sparse_expo) if c != 0.0}
+        if not terms:
+            terms = {tuple(self.sparse_expo[0]): 0.0}
+        tape = horner_tape(terms)
+        if 2 * len(tape) > MAX_COEF:
+            raise ValueError("polynomial too large for the Horner-tape epilogue (%d steps > %d)" % (len(tape), MAX_COEF // 2))
+        ep.kind, ep.nterms = EPI_HORNER, len(tape)
+        _write_tape(ep, 0, tape)
         return ep
 
     # ------------------------------------------------------------------ per-irrep feature epilogues
-    def feature_epilogues(self, row_scales, stride: int):
-        """Yields (epilogue, first output column) for batches of irreps: Phi[:, l*stride + p] = row_scales[l] chi_l."""
-        from ._lib import EPI_FEAT_CHEB1, EPI_FEAT_SPARSE
+    def feature_epilogues(self, row_scales, stride: int, monomial_list: bool = False):
+        """Yields (epilogue, first output column) for batches of irreps: Phi[:, l*stride + p] = row_scales[l] chi_l.
+        Rows of rank >= 2 are nested-Horner tapes (FEAT_HORNER, the pairwise kernel) or, with `monomial_list`, plain
+        (coefficient, exponents) lists (FEAT_SPARSE, what the homogeneous-space kernel averages over subgroup samples)."""
+        from ._lib import EPI_FEAT_CHEB1, EPI_FEAT_HORNER, EPI_FEAT_SPARSE
         scales = np.asarray(row_scales, dtype=np.float64)
         L = len(self.irreps)
         rows = []
@@ -306,8 +305,9 @@ class GroupPlan:
                 rows.append([float(scales[l] * self.M[l, k]) for k in range(deg + 1)])
             else:
                 expo = self.monos if self.kind == "rank2" else self.sparse_expo
-                terms = [(float(scales[l] * self.M[l, t]), expo[t]) for t in np.nonzero(self.M[l])[0]]
-                rows.append(terms if terms else [(0.0, expo[0])])
+                terms = {tuple(expo[t]): float(scales[l] * self.M[l, t]) for t in np.nonzero(self.M[l])[0]}
+                terms = terms if terms else {tuple(expo[0]): 0.0}
+                rows.append([(c, _pack_exponents(e)) for e, c in terms.items()] if monomial_list else horner_tape(terms))
         cap = MAX_COEF if self.kind == "cheb1" else MAX_COEF // 2
         start = 0
         while start < L:
@@ -318,23 +318,19 @@ class GroupPlan:
             if stop == start:
                 raise ValueError("irrep %d has too many polynomial terms for the feature epilogue" % start)
             ep = self._base_epilogue()
-            ep.kind = EPI_FEAT_CHEB1 if self.kind == "cheb1" else EPI_FEAT_SPARSE
+            ep.kind = EPI_FEAT_CHEB1 if self.kind == "cheb1" else EPI_FEAT_SPARSE if monomial_list else EPI_FEAT_HORNER
             ep.nterms = stop - start
             ep.feat_stride = stride
             pos = 0
             for i, l in enumerate(range(start, stop)):
                 ep.row_len[i] = len(rows[l])
-                for item in rows[l]:
-                    if self.kind == "cheb1":
+                if self.kind == "cheb1":
+                    for item in rows[l]:
                         ep.coef[pos] = item
-                    else:
-                        c, e = item
-                        packed = 0
-                        for j, ej in enumerate(e):
-                            packed |= int(ej) << (8 * j)
-                        ep.coef[2 * pos] = c
-                        ep.coef[2 * pos + 1] = np.array([packed], dtype=np.uint64).view(np.float64)[0]
-                    pos += 1
+                        pos += 1
+                else:
+                    _write_tape(ep, pos, rows[l])
+                    pos += len(rows[l])
             yield ep, start * stride
             start = stop
 
@@ -401,6 +397,45 @@ class GroupPlan:
             fast = fast * s2 + inner
         denom = np.maximum(np.abs(robust), 1e-300)
         return bool(np.max(np.abs(fast - robust) / denom) < tol)
+
+
+def horner_tape(terms: dict):
+    """Nested-Horner evaluation order of a sparse polynomial {exponent tuple: coefficient} as a list of (c, op) steps
+    for `epi_tape` (csrc/lsk_pairwise.cu): variable 0 is the innermost level; one step per node of the exponent trie,
+    missing exponents inside a chain cost one multiplication (inner level: a zero coefficient)."""
+    nv = len(next(iter(terms)))
+
+    def rec(sub, level):
+        if level == 0:
+            top = max(e[0] for e in sub)
+            return [(sub.get((e,), 0.0), 1 if e == top else 0) for e in range(top, -1, -1)]
+        groups = {}
+        for ex, c in sub.items():
+            groups.setdefault(ex[-1], {})[ex[:-1]] = c
+        top, base, out = max(groups), 2 + 3 * (level - 1), []
+        for e in range(top, -1, -1):
+            if e in groups:
+                out += rec(groups[e], level - 1)
+                out.append((0.0, base + (1 if e == top else 0)))
+            else:
+                out.append((0.0, base + 2))
+        return out
+
+    return rec(terms, nv - 1)
+
+
+def _pack_exponents(e) -> int:
+    packed = 0
+    for j, ej in enumerate(e):
+        assert 0 <= ej < 256
+        packed |= int(ej) << (8 * j)
+    return packed
+
+
+def _write_tape(ep: LskEpilogue, pos: int, tape):
+    for t, (c, op) in enumerate(tape):
+        ep.coef[2 * (pos + t)] = c
+        ep.coef[2 * (pos + t) + 1] = np.array([op], dtype=np.uint64).view(np.float64)[0]
 
 
 def _dot_long(w: np.ndarray, M: np.ndarray) -> np.ndarray:

@@ -25,9 +25,15 @@ int so5_stair_launch(const double* A, const double* B, int n_rows, int n_cols, i
                      const LskEpilogue& p, int sms, cudaStream_t stream);
 
 constexpr int PANEL_STAGE = KG_PER_STAGE * PANEL * 4;            // one panel, one stage: 2048 doubles = 16 KB
-constexpr int A_STAGE = (BM / PANEL) * PANEL_STAGE;              // two A panels
 constexpr int B_STAGE = PANEL_STAGE;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * 8 + 2 * STAGES * 8 + 64;
+// per tile variant (MT = 8-row fragments per warp): A panels per stage, ring depth, dynamic shared memory.  The 64-row
+// variant serves problems with many forms (five or more chunks per tile): its smaller stages buy a ring deep enough to
+// prefetch a whole tile during the previous tile's epilogue.
+template <int MT> struct TileCfg {
+    static constexpr int A_STAGE = (MT / 2) * PANEL_STAGE;
+    static constexpr int NST = MT == 4 ? STAGES : 7;
+    static constexpr int SMEM_BYTES = NST * (A_STAGE + B_STAGE) * 8 + 2 * NST * 8 + 64;
+};
 
 // ------------------------------------------------------------------------------------------------------------
 // epilogues: R entries per call so that every uniform coefficient load feeds R DFMAs
@@ -128,30 +134,48 @@ __device__ __forceinline__ void epi_orbit2(const LskEpilogue& p, const double (&
     for (int r = 0; r < R; ++r) out[r] = acc[r];
 }
 
+// Nested Horner over a run-time "tape" (any number of variables, any sparsity pattern): step t is (c, op) =
+// (tape[2t], low word of tape[2t+1]);  a_l is the accumulator of nesting level l (variable v_l, level 0 innermost):
+//   op 0: a_0 = a_0 v_0 + c        op 1: a_0 = c                      (coefficient chain of the innermost variable)
+//   op 2 + 3(l-1): a_l = a_l v_l + a_{l-1}     +1: a_l = a_{l-1}     +2: a_l = a_l v_l   (close a level-(l-1) chain / gap)
+// The result is a_{NV-1}.  One step = R fp64 operations for one uniform (c, op) fetch; all branches are warp-uniform.
+// The host (classfn.horner_tape) emits one step per node of the exponent trie, so a polynomial with T terms costs about
+// T + (number of distinct exponent prefixes) fused multiply-adds instead of T * degree multiplications.
 template <int R, int NV>
-__device__ __forceinline__ void epi_sparse(const double* coef, int nterms, const double (&v)[NV][R], double (&out)[R]) {
-    double acc[R];
+__device__ __forceinline__ void epi_tape(const double* tape, int nsteps, const double (&v)[NV][R], double (&out)[R]) {
+    double a[NV][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0;
-    for (int t = 0; t < nterms; ++t) {
-        const double c = coef[2 * t];
-        const unsigned long long e = (unsigned long long)__double_as_longlong(coef[2 * t + 1]);
-        double m[R];
+    for (int l = 0; l < NV; ++l)
 #pragma unroll
-        for (int r = 0; r < R; ++r) m[r] = c;
+        for (int r = 0; r < R; ++r) a[l][r] = 0.0;
+    for (int t = 0; t < nsteps; ++t) {
+        const double c = tape[2 * t];
+        const int op = (int)__double_as_longlong(tape[2 * t + 1]);
+        if (op == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int ei = (int)((e >> (8 * i)) & 0xffu);
-            for (int k = 0; k < ei; ++k) {
+            for (int r = 0; r < R; ++r) a[0][r] = fma(a[0][r], v[0][r], c);
+        } else if (op == 1) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) m[r] *= v[i][r];
+            for (int r = 0; r < R; ++r) a[0][r] = c;
+        } else {
+#pragma unroll
+            for (int l = 1; l < NV; ++l) {
+                const int base = 2 + 3 * (l - 1);
+                if (op == base) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) a[l][r] = fma(a[l][r], v[l][r], a[l - 1][r]);
+                } else if (op == base + 1) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) a[l][r] = a[l - 1][r];
+                } else if (op == base + 2) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) a[l][r] *= v[l][r];
+                }
             }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] += m[r];
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) out[r] = acc[r];
+    for (int r = 0; r < R; ++r) out[r] = a[NV - 1][r];
 }
 
 // k-groups of one form are cut into ceil(len / KG_PER_STAGE) chunks of nearly equal size (one pipeline stage each)
@@ -162,7 +186,7 @@ __device__ __forceinline__ int chunk_len(int remaining) {
 
 // ------------------------------------------------------------------------------------------------------------
 // main kernel
-//   EPI: epilogue kind;  NF: number of bilinear forms;  NV: number of variables (SPARSE only);  D: ORBIT2 size
+//   EPI: epilogue kind;  NF: number of bilinear forms;  NV: number of variables (HORNER kinds);  D: ORBIT2 size
 // ------------------------------------------------------------------------------------------------------------
 //   MT:  8-row accumulator fragments per warp (4: 128 x 64 tile, two A panels;  2: 64 x 64 tile, one A panel - for
 //        problems with three or four bilinear forms, whose accumulators would not fit in registers otherwise)
@@ -173,11 +197,12 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 double* __restrict__ out, long long ld_out,
                 const __grid_constant__ LskEpilogue p)
 {
+    constexpr int A_STAGE = TileCfg<MT>::A_STAGE, NST = TileCfg<MT>::NST;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
-    double* sB = sA + STAGES * A_STAGE;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
-    uint64_t* empty_bar = full_bar + STAGES;
+    double* sB = sA + NST * A_STAGE;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + NST * B_STAGE);
+    uint64_t* empty_bar = full_bar + NST;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int BMT = 32 * MT;                    // rows per CTA tile
     static_assert(MT == 4 || (MT == 2 && !SYM), "the triangular schedule assumes 128 x 64 tiles");
@@ -202,7 +227,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -210,7 +235,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 
     // ===================== producer duty (lane 0 of warp 0), folded into a consumer warp =====================
     // 16 consumer warps = 4 per SM sub-partition keeps the register budget at 128/thread; a 17th warp would cut it to 96.
-    // The producer state runs ahead of the consumer state by at most STAGES chunks.
+    // The producer state runs ahead of the consumer state by at most NST chunks.
     long long p_tile = blockIdx.x;
     int p_form = 0, p_group = p.group_begin[0], p_stage = 0;
     uint32_t p_phase = 0;
@@ -240,7 +265,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             if (++p_form == NF) { p_form = 0; p_tile += gridDim.x; }
             p_group = p.group_begin[p_form];
         }
-        if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
+        if (++p_stage == NST) { p_stage = 0; p_phase ^= 1; }
         ++issued_ahead;
         return true;
     };
@@ -249,7 +274,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)          // two attempts per call site keep the ring full and the code small
-                if (issued_ahead < STAGES) produce_once(false);
+                if (issued_ahead < NST) produce_once(false);
         }
     };
     // the chunk a warp is about to wait for must be in flight: warp-uniform poll loop (the vote makes the trip count
@@ -330,7 +355,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);      // hand the stage back to the producer
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == NST) { stage = 0; phase ^= 1; }
                 --issued_ahead;
             }
         }
@@ -393,13 +418,13 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                     }
                 }
             }
-            if constexpr (EPI == LSK_EPI_FEAT_CHEB1 || EPI == LSK_EPI_FEAT_SPARSE) {
+            if constexpr (EPI == LSK_EPI_FEAT_CHEB1 || EPI == LSK_EPI_FEAT_HORNER) {
                 // one output column block per irrep: Phi[i, l * feat_stride + j]
                 int pos = 0;
                 for (int l = 0; l < p.nterms; ++l) {
                     const int len = p.row_len[l];
                     if constexpr (EPI == LSK_EPI_FEAT_CHEB1) epi_cheb1<R>(p.coef + pos, len, var[0], res);
-                    else epi_sparse<R, NV>(p.coef + 2 * pos, len, var, res);
+                    else epi_tape<R, NV>(p.coef + 2 * pos, len, var, res);
                     pos += len;
 #pragma unroll
                     for (int e = 0; e < R; e += 2) {
@@ -410,7 +435,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             } else {
                 if constexpr (EPI == LSK_EPI_CHEB1) epi_cheb1<R>(p.coef, p.nterms, var[0], res);
                 else if constexpr (EPI == LSK_EPI_STAIR2) epi_stair2<R>(p, var[0], var[1], res);
-                else if constexpr (EPI == LSK_EPI_SPARSE) epi_sparse<R, NV>(p.coef, p.nterms, var, res);
+                else if constexpr (EPI == LSK_EPI_HORNER) epi_tape<R, NV>(p.coef, p.nterms, var, res);
                 else if constexpr (EPI == LSK_EPI_LINEAR) {
 #pragma unroll
                     for (int e = 0; e < R; ++e) res[e] = var[0][e];
@@ -437,16 +462,16 @@ template <int EPI, int NF, int NV, int D, bool SYM = false, int MT = 4>
 static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                   const LskEpilogue& p, int max_ctas, cudaStream_t stream) {
     auto kern = pairwise_kernel<EPI, NF, NV, D, SYM, MT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<MT>::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const long long rt = (n_rows + 32 * MT - 1) / (32 * MT), cp = (n_cols + BN - 1) / BN;
     const long long tiles = SYM ? rt * cp - rt * (rt - 1) : rt * cp;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, TileCfg<MT>::SMEM_BYTES);
     if (per_sm < 1) per_sm = 1;
     const long long cap = (long long)max_ctas * per_sm;
     int grid = (int)(tiles < cap ? tiles : cap);
-    return (int)launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)SMEM_BYTES, stream, A, B, n_rows, n_cols, kg_total, out, ld_out, p);
+    return (int)launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)TileCfg<MT>::SMEM_BYTES, stream, A, B, n_rows, n_cols, kg_total, out, ld_out, p);
 }
 
 }  // namespace lsk
@@ -511,18 +536,21 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.nterms <= 16) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 16);
         if (p.nterms <= 20) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 20);
         return LSK_ESIZE;
-    case LSK_EPI_SPARSE:
+    case LSK_EPI_HORNER:
         if (p.nterms < 1 || 2 * p.nterms > LSK_MAX_COEF) return LSK_ESIZE;
-        if (p.nforms == 1 && p.nvars == 1) LSK_GO(LSK_EPI_SPARSE, 1, 1, 1);
-        if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_SPARSE, 2, 2, 1);
-        if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_SPARSE, 3, 3, 1);
-        if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_SPARSE, 4, 4, 1);
+        if (p.nforms == 1 && p.nvars == 1) LSK_GO(LSK_EPI_HORNER, 1, 1, 1);
+        if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_HORNER, 2, 2, 1);
+        if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_HORNER, 3, 3, 1);
+        if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_HORNER, 4, 4, 1);
         return LSK_EUNSUPPORTED;
     case LSK_EPI_LINEAR:
         if (p.nforms == 1 && p.nvars == 1) LSK_GO_SYM(LSK_EPI_LINEAR, 1, 1, 1);
         return LSK_EARG;
+    case LSK_EPI_SPARSE:
+    case LSK_EPI_FEAT_SPARSE:
+        return LSK_EUNSUPPORTED;        // monomial-list encoding: only lsk_homog_pairs reads it
     case LSK_EPI_FEAT_CHEB1:
-    case LSK_EPI_FEAT_SPARSE: {
+    case LSK_EPI_FEAT_HORNER: {
         if (p.nterms < 1 || p.nterms > LSK_MAX_ROWS || p.feat_stride < n_cols) return LSK_EARG;
         int tot = 0;
         for (int l = 0; l < p.nterms; ++l) { if (p.row_len[l] < 1) return LSK_EARG; tot += p.row_len[l]; }
@@ -531,9 +559,9 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
             LSK_GO(LSK_EPI_FEAT_CHEB1, 1, 1, 1);
         }
         if (2 * tot > LSK_MAX_COEF) return LSK_ESIZE;
-        if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_FEAT_SPARSE, 2, 2, 1);
-        if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_FEAT_SPARSE, 3, 3, 1);
-        if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_FEAT_SPARSE, 4, 4, 1);
+        if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_FEAT_HORNER, 2, 2, 1);
+        if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_FEAT_HORNER, 3, 3, 1);
+        if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_FEAT_HORNER, 4, 4, 1);
         return LSK_EUNSUPPORTED;
     }
     default:

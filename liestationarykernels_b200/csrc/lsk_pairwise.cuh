@@ -18,6 +18,9 @@
 #define LSK_EPI_FEAT_CHEB1  6   // per-irrep outputs, rank 1:  out[i, l*stride + j] = sum_k C_l[k] T_k(var0), row l has row_len[l] coefficients
 #define LSK_EPI_FEAT_SPARSE 7   // per-irrep outputs, any rank: row l is a sparse polynomial with row_len[l] terms (SPARSE encoding)
 
+#define LSK_EPI_HORNER      8   // any:     nested Horner over a tape of (coefficient, op) steps (lsk_pairwise.cu epi_tape)
+#define LSK_EPI_FEAT_HORNER 9   // per-irrep outputs, any rank: row l is a tape of row_len[l] steps
+
 #define LSK_OUT_ROW_MAJOR   0   // out[i * ld_out + j]
 #define LSK_OUT_PANEL_MAJOR 1   // operand layout of this kernel: [i / 64][j / 4][i % 64][j % 4], out_kg k-groups per row
 

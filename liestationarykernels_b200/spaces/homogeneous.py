@@ -129,7 +129,7 @@ class CompactHomogeneousSpace(AbstractManifold):
         else:
             target = torch.zeros((N, L * P), dtype=dtype, device=x.device)
             buf, ld = target, target.stride(0)
-        for ep, col_shift in self.plan.feature_epilogues(scales, P):
+        for ep, col_shift in self.plan.feature_epilogues(scales, P, monomial_list=True):
             ep.reserved = 1                                   # pair (phase, point): M = lift(phase)^T lift(x)
             if panel:
                 ep.out_layout, ep.out_kg = _lib.OUT_PANEL_MAJOR, target.kg

@@ -142,6 +142,18 @@ def run_epilogue(ep, forms):
                 e = (packed >> (8 * i)) & 0xFF
                 m = m * var[i] ** e
             res = res + m
+    elif ep.kind == _lib.EPI_HORNER:
+        a = [np.zeros_like(var[0]) for _ in range(ep.nvars)]
+        for t in range(ep.nterms):
+            c, op = coef[2 * t], int(np.array([coef[2 * t + 1]]).view(np.uint64)[0])
+            if op == 0:
+                a[0] = a[0] * var[0] + c
+            elif op == 1:
+                a[0] = np.full_like(var[0], c)
+            else:
+                lvl, kind = 1 + (op - 2) // 3, (op - 2) % 3
+                a[lvl] = a[lvl] * var[lvl] + a[lvl - 1] if kind == 0 else a[lvl - 1].copy() if kind == 1 else a[lvl] * var[lvl]
+        res = a[ep.nvars - 1]
     else:
         raise ValueError(ep.kind)
     return ep.scale * res
