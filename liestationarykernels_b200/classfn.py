@@ -255,7 +255,8 @@ class GroupPlan:
             if use_fast:
                 if not self.stair_ok:
                     raise ValueError("staircase table too large for the fast form")
-                coef = _dot_long(w, self.M)
+                coef = _dot_long(w, self.M) * float(scale)     # the scale is folded into the coefficients: one multiply
+                ep.scale = 1.0                                  # per entry less (the dedicated SO(5) kernel requires it)
                 ep.kind, ep.nterms = EPI_STAIR2, len(self.stair_rows)
                 ep.stair_shape = self.stair_shape
                 for slot, ln in enumerate(reversed(self.stair_rows)):

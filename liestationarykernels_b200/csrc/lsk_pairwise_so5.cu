@@ -5,7 +5,7 @@
 // reference chain space.py:62-85, so.py:136-168,288-293, spectral_kernel.py:45-54), with everything the generic kernel
 // decides at run time fixed at compile time:
 //   * operands are the standard SO(5) embedding [matrix (25 + 3 zeros) | Spin(5) rotor (16)] = 11 k-groups, so ONE
-//     pipeline stage holds the operands of a whole 128 x 64 tile (three 22.5 KB bulk copies, one mbarrier round trip
+//     pipeline stage holds the operands of a whole 128 x 64 tile (two bulk copies, 45 + 22.5 KB, one mbarrier round trip
 //     per tile) and the DMMA phase is straight-line code;
 //   * the variable map is s1 = (tr g - 1) / 2,  s2 = 4 <R_x, R_y>^2 - (tr g + 1) / 2  with immediate constants;
 //   * the staircase shape is a template constant: nested Horner is straight-line code, one DFMA per coefficient, the
@@ -173,7 +173,6 @@ stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_r
     const int b_off = 2 * PANEL_DBL + (wc * 16) * 4 + frag;
     const bool vec_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int once = p.nvars - 1;                            // = 1 (see stair_fixed)
-    const double scale = p.scale;
     const long long ld8 = 8 * ld_out;
 
     int stage = 0;
@@ -247,13 +246,13 @@ stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_r
 #pragma unroll
                 for (int e = 0; e < R; e += 2) {
                     const int ml = e >> 2, n = (e >> 1) & 1;
-                    st_cs_f64x2(tile_out + (2 * h + ml) * ld8 + n * 8, scale * res[e], scale * res[e + 1]);
+                    st_cs_f64x2(tile_out + (2 * h + ml) * ld8 + n * 8, res[e], res[e + 1]);
                 }
             } else {
 #pragma unroll
                 for (int e = 0; e < R; e += 2) {
                     const int row = row0 + (2 * h + (e >> 2)) * 8, col = col0 + ((e >> 1) & 1) * 8;
-                    const double r0 = scale * res[e], r1 = scale * res[e + 1];
+                    const double r0 = res[e], r1 = res[e + 1];
                     if (row < n_rows && col < n_cols) {
                         double* dst = out + (size_t)row * ld_out + col;
                         if constexpr (SYM) {      // mirror: entries strictly above the diagonal
@@ -306,6 +305,7 @@ int so5_stair_launch(const double* A, const double* B, int n_rows, int n_cols, i
     if (kg_total != KG || p.nforms != 2 || p.nvars != 2 || p.out_layout != LSK_OUT_ROW_MAJOR) return LSK_EUNSUPPORTED;
     if (p.group_begin[0] != 0 || p.group_end[0] != KG_MATRIX || p.group_begin[1] != KG_MATRIX || p.group_end[1] != KG) return LSK_EUNSUPPORTED;
     if (((p.reserved >> 8) & 0xff) != 0x2) return LSK_EUNSUPPORTED;                 // only the rotor form enters squared
+    if (p.scale != 1.0) return LSK_EUNSUPPORTED;                                     // the host folds the scale into the table
     const double want[2][3] = {{-0.5, 0.5, 0.0}, {-0.5, -0.5, 4.0}};
     for (int v = 0; v < 2; ++v)
         for (int i = 0; i < 3; ++i)

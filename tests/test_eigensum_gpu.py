@@ -130,3 +130,25 @@ def test_symmetric_mode_equals_general_mode(n):
     a = torch.randn(n, 100, dtype=torch.float64, device="cuda")
     pa = ops.PanelMatrix.from_dense(a)
     assert torch.equal(ops.gram(pa, pa), ops.gram(pa, ops.PanelMatrix.from_dense(a)))
+
+
+@pytest.mark.parametrize("order", [10, 20, 100])
+def test_so5_dedicated_kernel_output_layouts(order):
+    """The SO(5) staircase kernel (lsk_pairwise_so5.cu) on outputs that defeat its fast store path: a base pointer that
+    is not 16-byte aligned, an odd leading dimension, edge tiles in both directions; all must equal the plain call."""
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    space = _space("SO", 5, order)
+    kern = EigenbasisSumKernel(_measure(dict(kind="matern", dim=10, lengthscale=0.9, nu=1.5)), space)
+    kern.eval()
+    torch.manual_seed(order)
+    x, y = space.rand(259), space.rand(131)
+    with torch.no_grad():
+        ref = kern(x, y)
+        big = torch.full((259, 140), float("nan"), dtype=torch.float64, device="cuda")
+        got = kern(x, y, out=big[:, 3:134])                     # misaligned base, even leading dimension
+        assert torch.equal(got, ref) and torch.isnan(big[:, :3]).all() and torch.isnan(big[:, 134:]).all()
+        odd = torch.full((259, 133), float("nan"), dtype=torch.float64, device="cuda")
+        got = kern(x, y, out=odd[:, :131])                      # odd leading dimension
+        assert torch.equal(got, ref) and torch.isnan(odd[:, 131:]).all()
+        one = kern(x[:1], y[:1])
+        assert torch.equal(one, ref[:1, :1])
