@@ -18,6 +18,22 @@
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
 
+#ifdef LSK_TRACE
+// development build only (tools/trace_build.py): clock64 stamps of CTA 0 of the generic kernel
+#define LSK_GT_TILES 10
+#define LSK_GT_EVENTS 16
+__device__ long long g_lsk_gtrace[16][LSK_GT_TILES][LSK_GT_EVENTS];
+__device__ long long g_lsk_gissue[128];
+#define LSK_GSTAMP(ev) do { if (blockIdx.x == 0 && lane == 0 && tile_no < LSK_GT_TILES && (ev) < LSK_GT_EVENTS) g_lsk_gtrace[warp][tile_no][ev] = clock64(); } while (0)
+extern "C" int lsk_debug_gtrace(void* host, void* issue) {
+    cudaError_t e = cudaMemcpyFromSymbol(host, g_lsk_gtrace, sizeof(g_lsk_gtrace));
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMemcpyFromSymbol(issue, g_lsk_gissue, sizeof(g_lsk_gissue));
+}
+#else
+#define LSK_GSTAMP(ev) do { } while (0)
+#endif
+
 namespace lsk {
 
 // lsk_pairwise_so5.cu: LSK_EUNSUPPORTED when the problem is not one of the compiled SO(5) shapes
@@ -32,7 +48,7 @@ constexpr int B_STAGE = PANEL_STAGE;
 template <int MT> struct TileCfg {
     static constexpr int A_STAGE = (MT / 2) * PANEL_STAGE;
     static constexpr int NST = MT == 4 ? STAGES : 7;
-    static constexpr int SMEM_BYTES = NST * (A_STAGE + B_STAGE) * 8 + 2 * NST * 8 + 64;
+    static constexpr int SMEM_BYTES = NST * (A_STAGE + B_STAGE) * 8 + 2 * NST * 8 + 128;   // + producer state (16 ints)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -225,72 +241,92 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         pc = 2 * r + (int)(t - ((long long)r * col_panels - (long long)r * (r - 1)));
     };
 
+    // producer state in shared memory: [0] next chunk (CTA-local sequence number) to be issued, [1] chunks per tile,
+    // [2] chunks of this CTA, [4 + 3 f ..] per form: first chunk, floor chunk size, remainder (same cut as chunk_len():
+    // the first `remainder` chunks of a form are one k-group longer)
+    int* pstate = reinterpret_cast<int*>(empty_bar + NST);
+    int* next_q = pstate;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+        int cpt = 0;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const int len = p.group_end[f] - p.group_begin[f], cnt = (len + KG_PER_STAGE - 1) / KG_PER_STAGE;
+            pstate[4 + 3 * f] = cpt;
+            pstate[5 + 3 * f] = len / cnt;
+            pstate[6 + 3 * f] = len - (len / cnt) * cnt;
+            cpt += cnt;
+        }
+        pstate[0] = 0;
+        pstate[1] = cpt;
+        pstate[2] = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * cpt;      // < 2^31: checked by the host
         fence_barrier_init();
     }
     __syncthreads();
     pdl_wait();         // launched with programmatic serialisation: everything above overlapped the tail of the embedding kernel
 
-    // ===================== producer duty (lane 0 of warp 0), folded into a consumer warp =====================
-    // 16 consumer warps = 4 per SM sub-partition keeps the register budget at 128/thread; a 17th warp would cut it to 96.
-    // The producer state runs ahead of the consumer state by at most NST chunks.
-    long long p_tile = blockIdx.x;
-    int p_form = 0, p_group = p.group_begin[0], p_stage = 0;
-    uint32_t p_phase = 0;
-    int issued_ahead = 0;                       // chunks issued but not yet consumed by warp 0
+    // ===================== producer duty: shared by all warps, whoever gets there first =====================
+    // 16 consumer warps = 4 per SM sub-partition keeps the register budget at 128/thread (a 17th, dedicated producer warp
+    // costs spills).  The chunks of this CTA form one sequence q = 0, 1, ... (tile-major, then form, then chunk); chunk q
+    // lives in ring stage q % NST.  Lane 0 of ANY warp may issue the next chunk: it reads the shared counter, tests the
+    // stage's empty barrier and claims q with a compare-and-swap.  With a fixed producer warp that warp falls behind the
+    // others by its producer work, every other warp runs into the ring limit behind it and the whole CTA moves at the
+    // pace of its slowest warp (per-warp clock traces, profiles/README.md); with claiming, the warps that are ahead do
+    // the producer work and the laggard catches up.
     // One non-blocking attempt to issue the next chunk.  LOOP-FREE on purpose: a loop (even an inline-asm spin) under a
     // thread-divergent branch makes ptxas give up warp-uniformity for the whole enclosing tile loop, which moves the
     // epilogue's coefficient fetch from the uniform datapath (LDCU + uniform-register operands) to per-thread LDC and
     // costs ~15 % of its DFMA rate.  `wait_hw` = use the hardware-suspending try_wait instead of a plain test.
-    auto produce_once = [&](bool wait_hw) -> bool {
-        if (p_tile >= n_tiles) return true;                           // nothing left: treat as done
-        const bool free_slot = wait_hw ? mbar_try_wait_once(&empty_bar[p_stage], p_phase ^ 1)
-                                       : mbar_test(&empty_bar[p_stage], p_phase ^ 1);   // first ring pass: immediately true
-        if (!free_slot) return false;
-        int pr, pc;
-        tile_coords(p_tile, pr, pc);
-        const double* srcA0 = A + ((size_t)((MT / 2) * pr) * kg_total + p_group) * (PANEL * 4);   // operands are padded to
-        const double* srcA1 = srcA0 + (size_t)kg_total * (PANEL * 4);                              // ROW_PAD rows: both exist
-        const double* srcB = B + ((size_t)pc * kg_total + p_group) * (PANEL * 4);
-        const int ng = chunk_len(p.group_end[p_form] - p_group);
-        const uint32_t bytes = (uint32_t)ng * PANEL * 4 * 8;
-        mbar_expect_tx(&full_bar[p_stage], (MT / 2 + 1) * bytes);
-        bulk_g2s(sA + p_stage * A_STAGE, srcA0, bytes, &full_bar[p_stage]);
-        if constexpr (MT == 4) bulk_g2s(sA + p_stage * A_STAGE + PANEL_STAGE, srcA1, bytes, &full_bar[p_stage]);
-        bulk_g2s(sB + p_stage * B_STAGE, srcB, bytes, &full_bar[p_stage]);
-        p_group += ng;
-        if (p_group >= p.group_end[p_form]) {
-            if (++p_form == NF) { p_form = 0; p_tile += gridDim.x; }
-            p_group = p.group_begin[p_form];
-        }
-        if (++p_stage == NST) { p_stage = 0; p_phase ^= 1; }
-        ++issued_ahead;
-        return true;
-    };
-    // keep the ring full without ever blocking (thread 0; called wherever it is cheap)
-    auto produce_ahead = [&]() {
-        if (threadIdx.x == 0) {
+    auto try_issue = [&](bool wait_hw) {
+        const int q = *reinterpret_cast<volatile int*>(next_q);
+        if (q >= pstate[2]) return;
+        const int st = q % NST;
+        const uint32_t parity = (uint32_t)(((q / NST) & 1) ^ 1);  // previous use of the stage; first ring pass: immediately true
+        const bool free_slot = wait_hw ? mbar_try_wait_once(&empty_bar[st], parity) : mbar_test(&empty_bar[st], parity);
+        if (!free_slot) return;
+        if (atomicCAS(next_q, q, q + 1) != q) return;             // another warp took it
+        const int cpt = pstate[1], k = q / cpt, c = q - k * cpt;
+        int gb = p.group_begin[0], base = pstate[5], rem = pstate[6], cum = 0;
 #pragma unroll
-            for (int k = 0; k < 2; ++k)          // two attempts per call site keep the ring full and the code small
-                if (issued_ahead < NST) produce_once(false);
-        }
+        for (int f = 1; f < NF; ++f)
+            if (c >= pstate[4 + 3 * f]) { gb = p.group_begin[f]; base = pstate[5 + 3 * f]; rem = pstate[6 + 3 * f]; cum = pstate[4 + 3 * f]; }
+        const int i = c - cum;
+        const int g0 = gb + i * base + min(i, rem), ng = base + (i < rem ? 1 : 0);
+        int pr, pc;
+        tile_coords(blockIdx.x + (long long)k * gridDim.x, pr, pc);
+        const double* srcA0 = A + ((size_t)((MT / 2) * pr) * kg_total + g0) * (PANEL * 4);   // operands are padded to
+        const double* srcA1 = srcA0 + (size_t)kg_total * (PANEL * 4);                         // ROW_PAD rows: both exist
+        const double* srcB = B + ((size_t)pc * kg_total + g0) * (PANEL * 4);
+        const uint32_t bytes = (uint32_t)ng * PANEL * 4 * 8;
+#ifdef LSK_TRACE
+        if (blockIdx.x == 0 && q < 128) g_lsk_gissue[q] = clock64();
+#endif
+        mbar_expect_tx(&full_bar[st], (MT / 2 + 1) * bytes);
+        bulk_g2s(sA + st * A_STAGE, srcA0, bytes, &full_bar[st]);
+        if constexpr (MT == 4) bulk_g2s(sA + st * A_STAGE + PANEL_STAGE, srcA1, bytes, &full_bar[st]);
+        bulk_g2s(sB + st * B_STAGE, srcB, bytes, &full_bar[st]);
+    };
+    // keep the ring full without ever blocking (lane 0 of every warp; called wherever it is cheap)
+    auto produce_ahead = [&]() {
+        if (lane == 0) try_issue(false);
     };
     // the chunk a warp is about to wait for must be in flight: warp-uniform poll loop (the vote makes the trip count
-    // uniform; only thread 0 of the CTA ever polls, every other warp leaves after one iteration)
-    auto produce_blocking = [&]() {
-        bool need = (threadIdx.x == 0) && (issued_ahead == 0);
+    // uniform; normally the chunk was issued long ago and the loop body runs once)
+    auto ensure_issued = [&](int qc) {
         unsigned done = 0;
         while (!done) {
             unsigned ok = 1;
-            if (need) {
-                ok = produce_once(true) ? 1u : 0u;
-                if (ok) need = false;
+            if (lane == 0 && *reinterpret_cast<volatile int*>(next_q) <= qc) {
+                try_issue(true);
+                ok = *reinterpret_cast<volatile int*>(next_q) > qc ? 1u : 0u;
             }
             done = __all_sync(0xffffffffu, ok);
         }
     };
+#ifdef LSK_TRACE
+    int tile_no = -1;
+#endif
 
     // ===================== consumer warps: 4 (rows) x 4 (cols), warp tile 32 x 16 =====================
     const int wr = warp >> 2, wc = warp & 3;
@@ -299,9 +335,14 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     const int b_off = (wc * 16) * 4 + frag;
     const bool vec_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
-    int stage = 0;
+    int stage = 0, qc = 0;          // ring stage and sequence number of the chunk this warp consumes next
     uint32_t phase = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+#ifdef LSK_TRACE
+        ++tile_no;
+        int chunk_no = 0;
+#endif
+        LSK_GSTAMP(0);
         int pr, pc;
         tile_coords(t, pr, pc);
         double acc[NF][MT][2][2];
@@ -320,8 +361,13 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             for (int g = p.group_begin[f], ng; g < g_end; g += ng) {
                 ng = chunk_len(g_end - g);
                 produce_ahead();
-                produce_blocking();
+                ensure_issued(qc);
+                LSK_GSTAMP(1 + 2 * chunk_no);
                 mbar_wait(&full_bar[stage], phase);
+                LSK_GSTAMP(2 + 2 * chunk_no);
+#ifdef LSK_TRACE
+                ++chunk_no;
+#endif
                 const double* pa = sA + stage * A_STAGE + a_off;
                 const double* pb = sB + stage * B_STAGE + b_off;
                 if (ng == KG_PER_STAGE) {
@@ -356,10 +402,11 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);      // hand the stage back to the producer
                 if (++stage == NST) { stage = 0; phase ^= 1; }
-                --issued_ahead;
+                ++qc;
             }
         }
 
+        LSK_GSTAMP(13);
         // ---- class polynomial on the accumulator fragments, 8 entries at a time ----
         const int row0 = pr * BMT + wr * (8 * MT) + (lane >> 2);
         const int col0 = pc * BN + wc * 16 + 2 * (lane & 3);
@@ -471,6 +518,9 @@ static int launch(const double* A, const double* B, int n_rows, int n_cols, int 
     if (per_sm < 1) per_sm = 1;
     const long long cap = (long long)max_ctas * per_sm;
     int grid = (int)(tiles < cap ? tiles : cap);
+    long long cpt = 0;                                  // chunks per tile; the CTA-local chunk sequence number is an int
+    for (int f = 0; f < NF; ++f) cpt += (p.group_end[f] - p.group_begin[f] + KG_PER_STAGE - 1) / KG_PER_STAGE;
+    if (((tiles + grid - 1) / grid) * cpt > 0x7fffffffLL) return LSK_ESIZE;
     return (int)launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)TileCfg<MT>::SMEM_BYTES, stream, A, B, n_rows, n_cols, kg_total, out, ld_out, p);
 }
 
