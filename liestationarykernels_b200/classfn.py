@@ -280,9 +280,9 @@ class GroupPlan:
             return ep
         # sparse polynomial in nvars variables: nested-Horner tape (csrc/lsk_pairwise.cu `epi_tape`)
         coef = _dot_long(w, self.M)
-        terms = {tuple(e): float(c) for c, e in zip(coef, self.sparse_expo) if c != 0.0}
-        if not terms:
-            terms = {tuple(self.sparse_expo[0]): 0.0}
+        # every monomial of the plan is kept (zero coefficients included): the tape's structure then depends on group and
+        # order only, which is what lets lsk_pairwise_poly pick a generated straight-line epilogue by structure hash
+        terms = {tuple(e): float(c) for c, e in zip(coef, self.sparse_expo)}
         tape = horner_tape(terms)
         if 2 * len(tape) > MAX_COEF:
             raise ValueError("polynomial too large for the Horner-tape epilogue (%d steps > %d)" % (len(tape), MAX_COEF // 2))

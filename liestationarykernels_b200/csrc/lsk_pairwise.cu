@@ -17,6 +17,7 @@
 // block (one bulk copy) and (b) a DMMA A/B fragment (8 rows x 4 k) is one contiguous, conflict-free 256 B read.
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
+#include "lsk_generated_epilogues.cuh"
 
 #ifdef LSK_TRACE
 // development build only (tools/trace_build.py): clock64 stamps of CTA 0 of the generic kernel
@@ -206,7 +207,8 @@ __device__ __forceinline__ int chunk_len(int remaining) {
 // ------------------------------------------------------------------------------------------------------------
 //   MT:  8-row accumulator fragments per warp (4: 128 x 64 tile, two A panels;  2: 64 x 64 tile, one A panel - for
 //        problems with three or four bilinear forms, whose accumulators would not fit in registers otherwise)
-template <int EPI, int NF, int NV, int D, bool SYM, int MT>
+//   GEN: > 0 selects a generated straight-line epilogue (lsk_generated_epilogues.cuh) instead of the tape interpreter
+template <int EPI, int NF, int NV, int D, bool SYM, int MT, int GEN>
 __global__ void __launch_bounds__(THREADS, 1)
 pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 int n_rows, int n_cols, int kg_total,               // kg_total: k-groups per row of A and B
@@ -482,7 +484,10 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             } else {
                 if constexpr (EPI == LSK_EPI_CHEB1) epi_cheb1<R>(p.coef, p.nterms, var[0], res);
                 else if constexpr (EPI == LSK_EPI_STAIR2) epi_stair2<R>(p, var[0], var[1], res);
-                else if constexpr (EPI == LSK_EPI_HORNER) epi_tape<R, NV>(p.coef, p.nterms, var, res);
+                else if constexpr (EPI == LSK_EPI_HORNER) {
+                    if constexpr (GEN > 0) gen_epilogue<GEN, R, NV>(p, var, res);
+                    else epi_tape<R, NV>(p.coef, p.nterms, var, res);
+                }
                 else if constexpr (EPI == LSK_EPI_LINEAR) {
 #pragma unroll
                     for (int e = 0; e < R; ++e) res[e] = var[0][e];
@@ -505,10 +510,10 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     }
 }
 
-template <int EPI, int NF, int NV, int D, bool SYM = false, int MT = 4>
+template <int EPI, int NF, int NV, int D, bool SYM = false, int MT = 4, int GEN = 0>
 static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                   const LskEpilogue& p, int max_ctas, cudaStream_t stream) {
-    auto kern = pairwise_kernel<EPI, NF, NV, D, SYM, MT>;
+    auto kern = pairwise_kernel<EPI, NF, NV, D, SYM, MT, GEN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<MT>::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const long long rt = (n_rows + 32 * MT - 1) / (32 * MT), cp = (n_cols + BN - 1) / BN;
@@ -586,13 +591,25 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.nterms <= 16) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 16);
         if (p.nterms <= 20) LSK_GO(LSK_EPI_ORBIT2, 2, 2, 20);
         return LSK_ESIZE;
-    case LSK_EPI_HORNER:
+    case LSK_EPI_HORNER: {
         if (p.nterms < 1 || 2 * p.nterms > LSK_MAX_COEF) return LSK_ESIZE;
+        // a tape whose structure was known at build time runs as generated straight-line code
+        const unsigned long long h = gen_hash(p);
+        for (const GenEntry& g : LSK_GEN_TABLE) {
+            if (g.hash != h || g.nsteps != p.nterms || g.nforms != p.nforms || g.nvars != p.nvars) continue;
+            switch (g.id) {
+#define LSK_GEN_CASE(ID, NFV, NVV) case ID: return launch<LSK_EPI_HORNER, NFV, NVV, 1, false, ((NFV) >= 3 ? 2 : 4), ID>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st);
+                LSK_GEN_LIST(LSK_GEN_CASE)
+#undef LSK_GEN_CASE
+            default: break;
+            }
+        }
         if (p.nforms == 1 && p.nvars == 1) LSK_GO(LSK_EPI_HORNER, 1, 1, 1);
         if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_HORNER, 2, 2, 1);
         if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_HORNER, 3, 3, 1);
         if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_HORNER, 4, 4, 1);
         return LSK_EUNSUPPORTED;
+    }
     case LSK_EPI_LINEAR:
         if (p.nforms == 1 && p.nvars == 1) LSK_GO_SYM(LSK_EPI_LINEAR, 1, 1, 1);
         return LSK_EARG;

@@ -63,3 +63,24 @@ def test_character_at_identity_equals_dimension():
             w[l] = 1.0
             val = emulate.pairwise(plan, eye, eye, plan.epilogue(w, 1.0, form="robust" if plan.kind == "rank2" else "auto"))
             assert abs(val[0, 0] - dim) < 1e-9 * dim, (fam, n, sig)
+
+
+def test_generated_epilogues_match_host_plans():
+    """csrc/lsk_generated_epilogues.cuh (tools/gen_epilogues.py) is keyed by a hash of the tape structure the host emits:
+    regenerate it whenever `horner_tape` or the monomial sets change, or the kernels silently fall back to the interpreter."""
+    import os
+    import re
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_epilogues
+    text = open(gen_epilogues.OUT).read()
+    table = {int(m.group(1), 16): int(m.group(2)) for m in re.finditer(r"\{0x([0-9a-f]{16})ull, (\d+), \d+, \d+, \d+\}", text)}
+    from liestationarykernels_b200 import classfn
+    rng = np.random.default_rng(0)
+    for fam, n, order in gen_epilogues.COMBOS:
+        plan = classfn.GroupPlan(fam, n, order)
+        ep = plan.epilogue(rng.uniform(0.1, 1.0, len(plan.irreps)), 0.7)
+        ops = [int(np.array([ep.coef[2 * t + 1]]).view(np.uint64)[0]) for t in range(ep.nterms)]
+        h = gen_epilogues.fnv(ep.nvars, ops)
+        assert table.get(h) == ep.nterms, (fam, n, order)
