@@ -70,3 +70,32 @@ class PhaseShardedSampler:
 def feature_shard(num_features: int, world_size: int, rank: int):
     """Slice of the spherical-function features owned by `rank` (RandomFourierApproximation sharding)."""
     return row_shard(num_features, world_size, rank)
+
+
+class FeatureShardedSampler:
+    """Wraps a RandomFourierApproximation (hyperbolic / SPD spaces): every rank keeps a slice of the spherical functions
+    (lmd, shift, coeff) and of the two weight vectors, evaluates its partial sample with the fused feature kernel and
+    all-reduces the [N] vector (north_star: "the random-phase/feature sum is sharded ... NCCL allreduce")."""
+
+    def __init__(self, sampler):
+        ws, rk = world()
+        self.full = sampler
+        self.lo, self.hi = feature_shard(sampler.kernel.manifold.order, ws, rk)
+        self.world_size = ws
+
+    def __call__(self, x):
+        from . import ops
+        s = self.full
+        m = s.kernel.manifold
+        funcs = m.lb_eigenspaces
+        lo, hi = self.lo, self.hi
+        if hi > lo:
+            local = type(funcs)(funcs.exp.lmd[lo:hi].contiguous(), funcs.exp.shift[lo:hi].contiguous(), m, funcs.coeff[lo:hi].contiguous())
+            psi = m._features(m.to_group(x), local, s._scale(), "panel")
+            w = torch.cat((s.weights_real[lo:hi], -s.weights_imag[lo:hi])).reshape(1, -1)
+            part = ops.gram(psi, ops.PanelMatrix.from_dense(w))[:, 0].contiguous()
+        else:
+            part = torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)
+        if self.world_size > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        return part

@@ -53,6 +53,19 @@ with torch.no_grad():
     t1.record()
     torch.cuda.synchronize()
     res["single_gpu_sampler_ms"] = t0.elapsed_time(t1) / 5
+    # feature-sharded sampler on the non-compact spaces (RandomFourierApproximation), all-reduce over NCCL
+    from liestationarykernels_b200.prior_approximation import RandomFourierApproximation
+    from liestationarykernels_b200.spaces import HyperbolicSpace, SymmetricPositiveDefiniteMatrices
+    from liestationarykernels_b200.spectral_kernel import RandomFourierFeatureKernel
+    for tag, space, meas in (("h3", HyperbolicSpace(3, order=1000), MaternSpectralMeasure(3, 1.0, 2.5)),
+                             ("spd3", SymmetricPositiveDefiniteMatrices(3, order=1000), MaternSpectralMeasure(6, 1.0, 2.5))):
+        fk = RandomFourierFeatureKernel(meas, space)
+        fk.eval()
+        fs = RandomFourierApproximation(fk)
+        pts = space.rand(2048)
+        ref = fs(pts)
+        got = D.FeatureShardedSampler(fs)(pts)
+        res["feature_sharded_%s_rel_diff" % tag] = ((got - ref).abs().max() / ref.abs().max()).item()
 res["world"] = world
 gathered = [None] * world
 dist.all_gather_object(gathered, res)
