@@ -138,6 +138,13 @@ int lsk_spd_features(const void* chol_upper, const void* shift_inv, const void* 
  * mode 1 = inverse (spaces/spd.py:66-67).  x, out: [num, n, n]; bad_count: device int32 (not PD / singular). */
 int lsk_small_matrix(const void* x, long long num, int n, int mode, void* out, void* bad_count, void* stream);
 
+/* Feature map of the flat torus [0,1)^dim (reference spaces/torus.py:14-97): panel-major [num, 2 * order] operand with
+ *   F[i, 2k] = w_k cos(two_pi * freq_k . x_i),  F[i, 2k+1] = w_k sin(two_pi * freq_k . x_i)      (w = 1 when weight is NULL),
+ * so that sum_k a_k Re chi_k(x_i - y_j) (TorusCharacter.chi, torus.py:91-95, summed as in spectral_kernel.py:45-54) is one
+ * LINEAR lsk_pairwise_poly of F(x; w = a) and F(y).  x: [num, dim]; freq: [order, dim] float64; out_kg >= ceil(2 order / 4). */
+int lsk_torus_features(const void* x, long long num, int dim, const void* freq, const void* weight, int order,
+                       double two_pi, void* out, int out_kg, void* stream);
+
 /* Haar samples from Gaussian draws: Householder QR (LAPACK conventions), q *= sign(diag r) (SU: conjugate phase),
  * q[:, :, 0] *= sign(det q) (SU: conjugate phase of det) - the deterministic part of SO.rand / SU.rand / SPD.rand_phase
  * (reference spaces/so.py:93-100, spaces/su.py:56-64, spaces/spd.py:48-55).  gauss, out: [num, n, n] float64 or complex128. */

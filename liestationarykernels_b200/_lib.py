@@ -76,6 +76,8 @@ _PROTOTYPES = {
     "lsk_haar_from_gaussian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                               ctypes.c_void_p]),
     "lsk_quaternion_to_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "lsk_torus_features": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "lsk_pairwise_poly": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
                                          ctypes.POINTER(LskEpilogue), ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
 }

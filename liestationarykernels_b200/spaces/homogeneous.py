@@ -144,8 +144,25 @@ class CompactHomogeneousSpace(AbstractManifold):
     def _eigensum(self, kernel, x, y, normalize, out=None):
         """EigenbasisSumKernel on M (spectral_kernel.py:37-54 with space.py:131-135, 273-275)."""
         from ..spectral_kernel import spectral_weights
-        w = spectral_weights(kernel.measure, self) * self._dims
+        w = spectral_weights(kernel.measure, self)
         scale = float(torch.abs(kernel.measure.variance[0]).item() / float(kernel.normalizer)) if normalize else 1.0
+        return self._eigensum_coefs(x, y, w, scale, out)
+
+    def _identity_values(self):
+        """phi_l(id, id) = d_l mean_k Re chi_l(h_k^T) for every irrep: the value each irrep contributes to the kernel at
+        coinciding points, i.e. to the normaliser (spectral_kernel.py:33-35).  Fixed by the subgroup samples; cached."""
+        key = (self.h_samples.data_ptr(), self.h_samples._version)
+        if getattr(self, "_identity_cache", (None, None))[0] != key:
+            eye = torch.zeros((1, self.n, self.m), dtype=dtype, device=self.h_samples.device)
+            eye[0, :self.m, :self.m] = torch.eye(self.m, dtype=dtype, device=eye.device)
+            vals = self._phase_features(eye, eye, np.ones(len(self.plan.irreps)), False).reshape(-1)
+            self._identity_cache = (key, vals)
+        return self._identity_cache[1]
+
+    def _eigensum_coefs(self, x, y, coefs, scale, out=None):
+        """scale * sum_l coefs[l] phi_l(x_i, y_j) for explicit per-irrep coefficients (the differentiable kernel path
+        evaluates this once with c(theta) and once per hyper-parameter with dc/dtheta)."""
+        w = np.asarray(coefs, dtype=np.float64) * self._dims
         ep = self.plan.collapsed_row_epilogue(w, scale)
         ep.out_layout = _lib.OUT_ROW_MAJOR
         gx = self.M_to_G(x)

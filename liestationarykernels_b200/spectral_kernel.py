@@ -93,11 +93,12 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
             if normalize:
                 self.compute_normalizer()
         manifold = self.manifold
+        params = self._hyper_parameters()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params) and \
+                (isinstance(manifold, CompactLieGroup) or hasattr(manifold, "_eigensum_coefs")):
+            return _WeightedCharacterSum.apply(self, x, y, normalize, out, *params)
         if not isinstance(manifold, CompactLieGroup):
             return manifold._eigensum(self, x, y, normalize, out)
-        params = self._hyper_parameters()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _WeightedCharacterSum.apply(self, x, y, normalize, out, *params)
         plan = manifold.plan
         ep = self._epilogue(normalize)
         same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides
@@ -124,12 +125,19 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
             a = torch.exp(-ls * ls / 2.0 * lam)
         if not normalize:
             return a
-        dims = torch.as_tensor(self.manifold._dims, dtype=dtype, device=a.device)
-        norm = (a * dims * dims).sum() if self.training else torch.as_tensor(self.normalizer, dtype=dtype, device=a.device).detach()
+        if not self.training:
+            norm = torch.as_tensor(self.normalizer, dtype=dtype, device=a.device).detach()
+        elif isinstance(self.manifold, CompactLieGroup):
+            dims = torch.as_tensor(self.manifold._dims, dtype=dtype, device=a.device)
+            norm = (a * dims * dims).sum()
+        else:       # homogeneous space: phi_l(id, id) = d_l * (subgroup average of chi_l), fixed by the h samples
+            norm = (a * self.manifold._identity_values().to(a.device)).sum()
         return torch.abs(var[0]) * a / norm
 
     def _evaluate(self, x, y, coefs, out):
         manifold = self.manifold
+        if not isinstance(manifold, CompactLieGroup):
+            return manifold._eigensum_coefs(x, y, np.asarray(coefs, dtype=np.float64), 1.0, out)
         plan = manifold.plan
         ep = plan.epilogue(np.asarray(coefs, dtype=np.float64) * manifold._dims, 1.0, form=self.form)
         same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides

@@ -297,6 +297,46 @@ class Homogeneous:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# spaces/torus.py — the flat torus [0,1)^n as a compact Lie group
+# ----------------------------------------------------------------------------------------------------------
+class Torus:
+    """torus.py:14-97.  Irreps are integer frequency vectors k; chi_k(x) = exp(2 pi i k.x), dimension 1, eigenvalue
+    4 pi^2 |k|^2 (exact pi); the character itself uses the reference's module constant `pi = 2 * acos(0)` evaluated in
+    float32 (torus.py:11), i.e. 3.1415927410125732."""
+
+    def __init__(self, n, order=20):
+        import itertools
+        self.n, self.dim, self.order = n, n, order
+        self.id = torch.zeros(n, dtype=F64).view(1, n)
+        vals = range(-order // 2, order // 2 + 1)                           # torus.py:55-57
+        sigs = list(itertools.product(vals, repeat=n))
+        spaces = [(sig, 1, 4 * math.pi * math.pi * sum(v ** 2 for v in sig)) for sig in sigs]    # torus.py:78-82
+        spaces.sort(key=lambda t: t[2])                                     # space.py:36-38: stable sort, first `order`
+        self.irreps = spaces[:order] if order else []
+
+    def rand(self, num=1):                                                  # torus.py:52-53
+        return torch.rand((num, self.n), dtype=F64)
+
+    def pairwise_embed(self, x, y):                                         # torus.py:39-43
+        xa, ya = pair_grid(x, y)
+        return xa.reshape(-1, self.n) - ya.reshape(-1, self.n)
+
+    def phase_function(self, irrep, diff):                                  # torus.py:91-95 + space.py:260-262 (d = 1)
+        k = torch.tensor(irrep[0], dtype=F64)
+        t = torch.sum(diff * k[:, ...], dim=1)
+        return torch.pow(torch.e, 2 * REF_PI * 1j * t)
+
+    def dist(self, x, y):                                                   # torus.py:32-36
+        d = torch.abs(x - y)
+        return torch.norm(torch.minimum(d, 1 - d), dim=1)
+
+    def pairwise_dist(self, x, y):                                          # torus.py:45-50 (no abs: as the reference)
+        d = self.pairwise_embed(x, y)
+        d = torch.minimum(d, 1 - d)
+        return torch.norm(d, dim=1).reshape(x.shape[0], y.shape[0])
+
+
+# ----------------------------------------------------------------------------------------------------------
 # spectral_kernel.py:26-54 — EigenbasisSumKernel
 # ----------------------------------------------------------------------------------------------------------
 def eigensum_unnormalised(space, measure, x, y):

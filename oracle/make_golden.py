@@ -86,6 +86,31 @@ def main(only=None):
                         irreps=[(e.index, e.dimension, e.lb_eigenvalue) for e in space.lb_eigenspaces]))
         print("   %.1fs" % (time.time() - t0), flush=True)
 
+    # ------------------------------------------------------------------ EigenbasisSumKernel on the flat torus (spaces/torus.py)
+    from lie_stationary_kernels.spaces.torus import Torus
+    torus_cases = [
+        ("eigsum_torus2_matern_L20", 2, 20, dict(kind="matern", dim=2, lengthscale=0.3, nu=2.5), 96, 70),
+        ("eigsum_torus3_heat_L31", 3, 31, dict(kind="heat", dim=3, lengthscale=0.2, variance=1.7), 64, 64),
+        ("eigsum_torus1_heat_L15", 1, 15, dict(kind="heat", dim=1, lengthscale=0.1), 50, 41),
+    ]
+    for name, n, order, mspec, nx, ny in torus_cases:
+        if not want(name):
+            continue
+        torch.manual_seed(4321)
+        space = Torus(n, order=order)
+        kern = EigenbasisSumKernel(measure_of(mspec), space)
+        kern.eval()
+        x, y = space.rand(nx), space.rand(ny)
+        y[:3] = x[:3]
+        with torch.no_grad():
+            k_norm = kern(x, y)
+            k_raw = kern(x, y, normalize=False)
+            k_xx = kern(x[:8])
+        save(name, dict(group="Torus", n=n, order=order, measure=mspec, x=x, y=y,
+                        normalizer=kern.normalizer.detach().clone(), k_norm=k_norm, k_raw=k_raw, k_xx=k_xx,
+                        irreps=[(e.index, e.dimension, e.lb_eigenvalue) for e in space.lb_eigenspaces],
+                        pairwise_dist=space.pairwise_dist(x[:16], y[:12]), dist=space.dist(x[:16], y[:16])))
+
     # ------------------------------------------------------------------ torus representatives / characters (lie_groups.py tests)
     if want("chars"):
         torch.manual_seed(7)

@@ -64,6 +64,11 @@ def test_so5_forms_agree_with_golden(form):
     ("SO", 5, 20, dict(kind="matern", dim=10, lengthscale=1.0, nu=2.5), 70, 65),
     ("SU", 4, 20, dict(kind="heat", dim=15, lengthscale=1.0), 66, 70),
     ("SU", 3, 10, dict(kind="heat", dim=8, lengthscale=1.0), 64, 1),
+    # truncation orders without a generated epilogue: the run-time tape interpreter (epi_tape) and the rolled staircase loop
+    ("SU", 3, 7, dict(kind="matern", dim=8, lengthscale=1.2, nu=1.5), 70, 33),
+    ("SU", 4, 6, dict(kind="heat", dim=15, lengthscale=1.0), 65, 20),
+    ("SO", 4, 9, dict(kind="heat", dim=6, lengthscale=1.0), 40, 67),
+    ("SO", 5, 14, dict(kind="matern", dim=10, lengthscale=1.0, nu=2.5), 50, 66),
 ])
 def test_against_oracle_ragged_sizes(group, n, order, spec, nx, ny):
     """fresh seeded inputs, sizes that are not multiples of the 64x64 tile"""

@@ -125,3 +125,16 @@ def test_noncompact_matches_reference(name):
     assert scaled_err(gram, g["gram"]) < TOL
     sample = orc.rff_sample(space, meas, g["lmd"], g["shift"], g["w_re"], g["w_im"], g["x"], g["normalizer"])
     assert scaled_err(sample, g["sample"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["eigsum_torus2_matern_L20", "eigsum_torus3_heat_L31", "eigsum_torus1_heat_L15"])
+def test_torus_eigensum_matches_reference(name):
+    g = load_golden(name)
+    space = orc.Torus(g["n"], g["order"])
+    assert [(tuple(s), d, c) for s, d, c in space.irreps] == [(tuple(s), d, c) for s, d, c in g["irreps"]]
+    meas = _measure(g["measure"])
+    raw = orc.eigensum_unnormalised(space, meas, g["x"], g["y"])
+    assert scaled_err(raw, g["k_raw"]) < TOL
+    assert scaled_err(orc.eigensum(space, meas, g["x"], g["y"], g["normalizer"]), g["k_norm"]) < TOL
+    assert torch.equal(space.pairwise_dist(g["x"][:16], g["y"][:12]), g["pairwise_dist"])
+    assert torch.equal(space.dist(g["x"][:16], g["y"][:16]), g["dist"])
