@@ -25,8 +25,8 @@ extern "C" {
 #define LSK_ESIZE        (-2)   /* size out of supported range */
 #define LSK_EUNSUPPORTED (-3)   /* configuration not compiled  */
 
-#define LSK_MAX_FORMS 4
-#define LSK_MAX_VARS  4
+#define LSK_MAX_FORMS 5
+#define LSK_MAX_VARS  5
 #define LSK_MAX_COEF  400
 #define LSK_MAX_ROWS  24
 

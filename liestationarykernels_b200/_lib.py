@@ -13,8 +13,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblsk.so")
 
-MAX_FORMS = 4
-MAX_VARS = 4
+MAX_FORMS = 5
+MAX_VARS = 5
 MAX_COEF = 400
 MAX_ROWS = 24
 

@@ -75,8 +75,8 @@ class GroupPlan:
                     segs_b.append((k, 0))
             self.real_vars = rank
         else:
-            if n > 5:
-                raise NotImplementedError("SU(%d): needs more than %d real invariants" % (n, MAX_VARS))
+            if n > 6:
+                raise NotImplementedError("SU(%d): needs more than %d real invariants (supported: SU(2) ... SU(6))" % (n, MAX_VARS))
             # e_k for k <= n/2; e_{n-k} = conj(e_k); e_{n/2} is real for even n
             half = n // 2
             for k in range(1, half + 1):

@@ -7,6 +7,7 @@
 //     out[panel][k-group][row in panel (64)][4]      (doubles; rows beyond `num` and pad columns are zero)
 // It replaces the reference's `inv` + `cartesian_prod` + `bmm` operand preparation (space.py:62-78).
 #include "lsk_common.cuh"
+#include "lsk_pairwise.cuh"
 
 #define LSK_SEG_SPIN5 100     // segment code: rotor coefficients of the Spin(5) lift (n = 5, real)
 
@@ -14,11 +15,11 @@ namespace lsk {
 
 struct EmbedSpec {
     int nseg;
-    int wedge[4];        // 1, 2 or 3
-    int part[4];         // 0: real matrix;  1: complex (re, im);  2: complex (re, im) [B side, real form];
+    int wedge[LSK_MAX_FORMS];        // 1, 2 or 3
+    int part[LSK_MAX_FORMS];         // 0: real matrix;  1: complex (re, im);  2: complex (re, im) [B side, real form];
                          // 3: complex (-im, re) [B side, imaginary form];  4: real, Hodge star on the row index (n = 2k)
-    int group_begin[4];  // first k-group of the segment
-    int length[4];       // number of doubles in the segment (before padding to a multiple of 4)
+    int group_begin[LSK_MAX_FORMS];  // first k-group of the segment
+    int length[LSK_MAX_FORMS];       // number of doubles in the segment (before padding to a multiple of 4)
 };
 
 __device__ __forceinline__ int binom(int n, int k) {
@@ -285,9 +286,9 @@ namespace lsk {
 static int make_spec(long long num, int n, int is_complex, int nseg, const int* wedge, const int* part, const int* group_begin,
                      int kg_total, EmbedSpec& spec) {
     if (!wedge || !part || !group_begin) return LSK_EARG;
-    if (num < 0 || n < 1 || n > 8 || nseg < 1 || nseg > 4 || kg_total < 1) return LSK_ESIZE;
+    if (num < 0 || n < 1 || n > 8 || nseg < 1 || nseg > LSK_MAX_FORMS || kg_total < 1) return LSK_ESIZE;
     spec.nseg = nseg;
-    for (int s = 0; s < 4; ++s) { spec.wedge[s] = 1; spec.part[s] = 0; spec.group_begin[s] = 0; spec.length[s] = 0; }
+    for (int s = 0; s < LSK_MAX_FORMS; ++s) { spec.wedge[s] = 1; spec.part[s] = 0; spec.group_begin[s] = 0; spec.length[s] = 0; }
     for (int s = 0; s < nseg; ++s) {
         if (wedge[s] == LSK_SEG_SPIN5) {
             if (is_complex || n != 5 || part[s] != 0) return LSK_EARG;

@@ -64,6 +64,8 @@ def main(only=None):
         ("eigsum_su3_matern_L20", SU, 3, 20, dict(kind="matern", dim=8, lengthscale=1.0, nu=1.5), 32, 32),
         ("eigsum_su4_heat_L20", SU, 4, 20, dict(kind="heat", dim=15, lengthscale=1.0), 40, 36),
         ("eigsum_su5_heat_L10", SU, 5, 10, dict(kind="heat", dim=24, lengthscale=1.0), 16, 16),
+        ("eigsum_su6_heat_L10", SU, 6, 10, dict(kind="heat", dim=35, lengthscale=1.0), 14, 12),
+        ("eigsum_su6_matern_L20", SU, 6, 20, dict(kind="matern", dim=35, lengthscale=1.5, nu=2.5), 12, 12),
         ("eigsum_so4_heat_L20", SO, 4, 20, dict(kind="heat", dim=6, lengthscale=1.0), 24, 24),
         ("eigsum_so6_heat_L20", SO, 6, 20, dict(kind="heat", dim=15, lengthscale=1.0), 20, 20),
     ]

@@ -26,13 +26,24 @@ def test_library_exports_every_declared_symbol():
     assert lib.lsk_version() >= 100
 
 
-def test_epilogue_struct_layout_matches_header():
+def test_epilogue_struct_layout_matches_header(tmp_path):
+    """The ctypes mirror of LskEpilogue against what a C compiler makes of include/lsk.h."""
+    import os
+    import subprocess
     from liestationarykernels_b200 import _lib
-    # C layout: 4 + 4 + 4 + 24 + 4 int32 = 40 ints = 160 bytes, then 1 + 4*5 + 400 doubles
-    assert ctypes.sizeof(_lib.LskEpilogue) == 160 + 8 * (2 + 20 + 400)
-    assert _lib.LskEpilogue.scale.offset == 160
-    assert _lib.LskEpilogue.coef.offset == 160 + 8 * 22
-    assert ctypes.sizeof(_lib.LskEpilogue) < 4096, "must fit the kernel-parameter constant bank"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lsk.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(LskEpilogue), offsetof(LskEpilogue, group_end), offsetof(LskEpilogue, row_len), offsetof(LskEpilogue, scale), '
+                   'offsetof(LskEpilogue, aff), offsetof(LskEpilogue, coef)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    c = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    E = _lib.LskEpilogue
+    assert c == [ctypes.sizeof(E), E.group_end.offset, E.row_len.offset, E.scale.offset, E.aff.offset, E.coef.offset]
+    # 4 + 5 + 5 + 24 + 4 int32 = 168 bytes, then scale, stair_shape, 5 x 6 affine map, 400 coefficients
+    assert E.scale.offset == 168 and E.coef.offset == 168 + 8 * 32
+    assert ctypes.sizeof(E) < 4096, "must fit the kernel-parameter constant bank"
 
 
 def test_argument_errors_without_gpu():
