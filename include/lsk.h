@@ -79,7 +79,7 @@ int lsk_version(void);
 /* Number of doubles of the panel-major embedding buffer for `num` points and `kg_total` k-groups. */
 long long lsk_embed_buffer_doubles(long long num, int kg_total);
 
-/* Per-point compound-matrix embeddings (k = 1..3) of SO(n)/SU(n) elements, panel-major output.
+/* Per-point compound-matrix embeddings (k = 1..3; k = 4 for real matrices) of SO(n)/SU(n) elements, panel-major output.
  * Replaces operand preparation of CompactLieGroup.pairwise_diff: inv + cartesian_prod + bmm (reference space.py:62-78,
  * utils.py:40-52, spaces/so.py:124-127, spaces/su.py:79-82).
  * x: [num, n, n] float64 (is_complex = 0) or complex128 (is_complex = 1).  wedge/part/group_begin: host int[nseg].

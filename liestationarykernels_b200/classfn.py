@@ -52,9 +52,9 @@ class GroupPlan:
         segs_a, segs_b = [], []        # (wedge, part)
         if self.family == "SO":
             rank = n // 2
-            if rank > 3:
-                raise NotImplementedError("SO(%d): compound matrices beyond Lambda^3 are not implemented "
-                                          "(supported: SO(3) ... SO(7))" % n)
+            if rank > 4:
+                raise NotImplementedError("SO(%d): compound matrices beyond Lambda^4 are not implemented "
+                                          "(supported: SO(3) ... SO(8))" % n)
             if n % 2 == 0:
                 # e_1..e_r from the compound matrices; for even r additionally z = prod 2 sin(theta_i), the invariant that
                 # separates the two SO(2r) classes with equal spectrum, as the Hodge-star form <*Lambda^r x, Lambda^r y>

@@ -28,8 +28,8 @@ __device__ __forceinline__ int binom(int n, int k) {
     return r;
 }
 
-// lexicographic rank -> increasing index tuple of size k (k <= 3) out of n
-__device__ __forceinline__ void unrank(int idx, int n, int k, int (&t)[3]) {
+// lexicographic rank -> increasing index tuple of size k (k <= 4) out of n
+__device__ __forceinline__ void unrank(int idx, int n, int k, int (&t)[4]) {
     int start = 0;
     for (int pos = 0; pos < k; ++pos) {
         for (int v = start; v < n; ++v) {
@@ -52,7 +52,7 @@ __device__ __forceinline__ void cmul(double ar, double ai, double br, double bi,
 }
 
 template <bool CPLX>
-__device__ void minor(const double* x, int n, int k, const int (&I)[3], const int (&J)[3], double& re, double& im) {
+__device__ void minor(const double* x, int n, int k, const int (&I)[4], const int (&J)[4], double& re, double& im) {
     if (k == 1) { load<CPLX>(x, n, I[0], J[0], re, im); return; }
     if (k == 2) {
         double ar, ai, br, bi, cr, ci, dr, di, p1r, p1i, p2r, p2i;
@@ -60,6 +60,26 @@ __device__ void minor(const double* x, int n, int k, const int (&I)[3], const in
         load<CPLX>(x, n, I[0], J[1], br, bi); load<CPLX>(x, n, I[1], J[0], cr, ci);
         cmul(ar, ai, dr, di, p1r, p1i); cmul(br, bi, cr, ci, p2r, p2i);
         re = p1r - p2r; im = p1i - p2i;
+        return;
+    }
+    if (k == 4) {
+        // 4 x 4 minor (SO(8): Lambda^4), real matrices only: Laplace expansion by complementary 2 x 2 minors of the two
+        // row pairs (rows 0,1 against rows 2,3)
+        double a[4][4];
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) { double t; load<CPLX>(x, n, I[r], J[c], a[r][c], t); }
+        double det = 0.0;
+        for (int c0 = 0; c0 < 4; ++c0)
+            for (int c1 = c0 + 1; c1 < 4; ++c1) {
+                int d0 = -1, d1 = -1;
+                for (int c = 0; c < 4; ++c)
+                    if (c != c0 && c != c1) { if (d0 < 0) d0 = c; else d1 = c; }
+                const double top = a[0][c0] * a[1][c1] - a[0][c1] * a[1][c0];
+                const double bot = a[2][d0] * a[3][d1] - a[2][d1] * a[3][d0];
+                const int sgn = ((c0 + c1 + 0 + 1) & 1) ? -1 : 1;       // (-1)^(row indices 0 + 1 + column indices c0 + c1)
+                det += sgn * top * bot;
+            }
+        re = det; im = 0.0;
         return;
     }
     // k == 3: cofactor expansion along the first row
@@ -210,24 +230,24 @@ embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ Embe
                 const int k = spec.wedge[seg], part = spec.part[seg];
                 const int C = binom(n, k);
                 const int el = CPLX ? (e >> 1) : e;
-                int I[3] = {0, 0, 0}, J[3] = {0, 0, 0};
+                int I[4] = {0, 0, 0, 0}, J[4] = {0, 0, 0, 0};
                 unrank(el / C, n, k, I);
                 unrank(el % C, n, k, J);
                 double hodge = 1.0;
                 if (!CPLX && part == 4) {
                     // Hodge star on the row index (n = 2k): I -> complement I^c, sign of the permutation (I, I^c)
-                    int comp[3] = {0, 0, 0}, nc = 0, inv = 0;
+                    int comp[4] = {0, 0, 0, 0}, nc = 0, inv = 0;
                     for (int v = 0; v < n; ++v) {
                         bool in = false;
                         for (int q = 0; q < k; ++q) in = in || (I[q] == v);
                         if (!in) {
                             for (int q = 0; q < k; ++q) inv += (I[q] > v);      // inversions between I and I^c
-                            if (nc < 3) comp[nc] = v;
+                            if (nc < 4) comp[nc] = v;
                             ++nc;
                         }
                     }
                     hodge = (inv & 1) ? -1.0 : 1.0;
-                    for (int q = 0; q < 3; ++q) I[q] = comp[q];
+                    for (int q = 0; q < 4; ++q) I[q] = comp[q];
                 }
                 double re, im;
                 minor<CPLX>(x + row * (long long)(CPLX ? 2 : 1) * n * n, n, k, I, J, re, im);
@@ -297,7 +317,7 @@ static int make_spec(long long num, int n, int is_complex, int nseg, const int* 
             if (s > 0 && group_begin[s] < spec.group_begin[s - 1] + (spec.length[s - 1] + 3) / 4) return LSK_EARG;
             continue;
         }
-        if (wedge[s] < 1 || wedge[s] > 3 || wedge[s] > n) return LSK_EARG;
+        if (wedge[s] < 1 || wedge[s] > 4 || wedge[s] > n || (wedge[s] == 4 && is_complex)) return LSK_EARG;
         if (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0 && !(part[s] == 4 && n == 2 * wedge[s]))) return LSK_EARG;
         int c = 1;
         for (int i = 1; i <= wedge[s]; ++i) c = c * (n - wedge[s] + i) / i;

@@ -66,6 +66,8 @@ def main(only=None):
         ("eigsum_su5_heat_L10", SU, 5, 10, dict(kind="heat", dim=24, lengthscale=1.0), 16, 16),
         ("eigsum_su6_heat_L10", SU, 6, 10, dict(kind="heat", dim=35, lengthscale=1.0), 14, 12),
         ("eigsum_su6_matern_L20", SU, 6, 20, dict(kind="matern", dim=35, lengthscale=1.5, nu=2.5), 12, 12),
+        ("eigsum_so8_heat_L20", SO, 8, 20, dict(kind="heat", dim=28, lengthscale=1.0), 12, 12),
+        ("eigsum_so8_matern_L10", SO, 8, 10, dict(kind="matern", dim=28, lengthscale=2.0, nu=1.5), 10, 12),
         ("eigsum_so4_heat_L20", SO, 4, 20, dict(kind="heat", dim=6, lengthscale=1.0), 24, 24),
         ("eigsum_so6_heat_L20", SO, 6, 20, dict(kind="heat", dim=15, lengthscale=1.0), 20, 20),
     ]

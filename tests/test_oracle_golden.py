@@ -17,7 +17,8 @@ def _measure(spec):
 
 EIG = ["eigsum_so3_heat_L20", "eigsum_so3_matern_L100", "eigsum_so5_heat_L20", "eigsum_so7_heat_L20",
        "eigsum_su2_heat_L20", "eigsum_su3_matern_L20", "eigsum_su4_heat_L20", "eigsum_su5_heat_L10",
-       "eigsum_so4_heat_L20", "eigsum_so6_heat_L20", "eigsum_su6_heat_L10", "eigsum_su6_matern_L20"]
+       "eigsum_so4_heat_L20", "eigsum_so6_heat_L20", "eigsum_su6_heat_L10", "eigsum_su6_matern_L20",
+       "eigsum_so8_heat_L20", "eigsum_so8_matern_L10"]
 
 
 @pytest.mark.parametrize("name", EIG)
