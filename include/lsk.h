@@ -43,6 +43,8 @@ extern "C" {
                                    op 0: a0 = a0 v0 + c;  1: a0 = c;  2+3(l-1): al = al vl + a(l-1);  +1: al = a(l-1);
                                    +2: al = al vl;  result a(nvars-1)  (SU(3..5), SO(4), SO(6), SO(7))               */
 #define LSK_EPI_FEAT_HORNER 9   /* per-irrep rows, any rank: row l is a tape of row_len[l] steps                  */
+#define LSK_EPI_SYRK       10   /* out += scale * form_0 on the tiles that reach the diagonal or lie above it (square
+                                   row-major output, nothing mirrored): trailing update of lsk_potrf_upper          */
 
 /* output layouts */
 #define LSK_OUT_ROW_MAJOR   0   /* out[i * ld_out + j]                                                            */
@@ -153,6 +155,23 @@ int lsk_haar_from_gaussian(const void* gauss, long long num, int n, int is_compl
 /* Unit-quaternion parametrisation of SO(3) (to_su2 = 0, reference spaces/so.py:74-92) or SU(2) (to_su2 = 1,
  * spaces/su.py:47-55).  gauss: [num, 4] float64;  out: [num, 3, 3] float64 or [num, 2, 2] complex128. */
 int lsk_quaternion_to_group(const void* gauss, long long num, int to_su2, void* out, void* stream);
+
+/* ---- GP regression step on the covariance (the caller of the hot path: reference examples/gpr_model.py:26-39 hands
+ * K + sigma_n^2 I to gpytorch.models.ExactGP / ExactMarginalLogLikelihood, i.e. to a LAPACK / cuSOLVER potrf + potrs) ---- */
+
+/* Workspace (doubles) of lsk_potrf_upper for an n x n matrix: the inverses of the 128 x 128 diagonal blocks of the factor
+ * (kept for lsk_potrs_upper) followed by one panel-major row panel. */
+long long lsk_potrf_work_doubles(long long n);
+
+/* Blocked fp64 Cholesky A = U^T U in place: on return the upper triangle of the row-major A [n, lda] holds U (the lower
+ * factor L = U^T of the same buffer read column-major); the strict lower triangle is scratch.  Only the upper triangle of
+ * A is read.  info_dev: device int32, 0 on success, else the 1-based index of the first non-positive pivot (LAPACK dpotrf).
+ * work: device, lsk_potrf_work_doubles(n) doubles, must be kept for lsk_potrs_upper. */
+int lsk_potrf_upper(void* A, long long n, long long lda, void* work, void* info_dev, void* stream);
+
+/* Triangular solves with the factor and workspace of lsk_potrf_upper, one right-hand side, in place in b [n]:
+ * which = 1: U^T y = b;  2: U x = b;  3: both (A x = b, LAPACK dpotrs).  tmp: device scratch, n doubles. */
+int lsk_potrs_upper(const void* U, long long n, long long lda, const void* work, void* b, void* tmp, int which, void* stream);
 
 #ifdef __cplusplus
 }

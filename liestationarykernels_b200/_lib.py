@@ -19,7 +19,7 @@ MAX_COEF = 400
 MAX_ROWS = 24
 
 EPI_CHEB1, EPI_STAIR2, EPI_ORBIT2, EPI_SPARSE, EPI_LINEAR, EPI_FEAT_CHEB1, EPI_FEAT_SPARSE = 1, 2, 3, 4, 5, 6, 7
-EPI_HORNER, EPI_FEAT_HORNER = 8, 9
+EPI_HORNER, EPI_FEAT_HORNER, EPI_SYRK = 8, 9, 10
 OUT_ROW_MAJOR, OUT_PANEL_MAJOR, FEAT_COMPLEX = 0, 1, 2
 
 
@@ -78,6 +78,11 @@ _PROTOTYPES = {
     "lsk_quaternion_to_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "lsk_torus_features": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "lsk_potrf_work_doubles": (ctypes.c_longlong, [ctypes.c_longlong]),
+    "lsk_potrf_upper": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
+    "lsk_potrs_upper": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "lsk_pairwise_poly": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
                                          ctypes.POINTER(LskEpilogue), ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
 }

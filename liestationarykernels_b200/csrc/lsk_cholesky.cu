@@ -1,0 +1,423 @@
+// Blocked fp64 Cholesky factorisation and triangular solves for the GP regression step that consumes the covariance
+// (the reference hands K + sigma_n^2 I to gpytorch's ExactGP, examples/gpr_model.py:26-39, whose
+// marginal likelihood / prediction is a LAPACK/cuSOLVER potrf + potrs).
+//
+//   A = U^T U,  U upper triangular, factorised IN PLACE in the upper triangle of a row-major matrix (equivalently: the
+//   lower factor L = U^T of the same matrix read column-major).  Right-looking, block size 128:
+//     diag_kernel   one CTA: U_kk = chol(A_kk) and W_kk = U_kk^{-1}, both register-resident rank-1 sweeps (each thread owns
+//                   a cyclic 4 x 8 sub-block; one row broadcast through shared memory and ONE barrier per step)
+//     trsm_kernel   row panel U_k,: = W_kk^T A_k,: on the fp64 tensor-core path (DMMA), written twice: row-major into A
+//                   (the factor) and panel-major into the workspace (the operand layout of the pairwise kernel)
+//     pairwise_kernel<SYRK>  trailing update A_ij -= U_ki^T U_kj on the tiles that reach the diagonal or lie above it
+//                   (lsk_pairwise.cu: TMA ring + DMMA, read-modify-write epilogue)
+//   The inverses W_kk stay in the workspace: the triangular solves U^T y = b, U x = y are then one small matrix-vector
+//   product per block plus a panel update (fwd_step_kernel / bwd_step_kernel), no divisions, no dependent chains.
+#include "lsk_common.cuh"
+#include "lsk_pairwise.cuh"
+
+extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows, long long n_cols, int kg_total,
+                                 const LskEpilogue* epi, void* out, long long ld_out, void* stream);
+
+namespace lsk {
+namespace chol {
+
+constexpr int NB = 128;                 // block size = K of the trailing update (32 k-groups)
+constexpr int WBLK = NB * NB;           // doubles per stored inverse block
+constexpr int SLD = NB + 1;             // padded row length of the shared-memory copy of U_kk
+constexpr int DIAG_SMEM = (NB * SLD + 2 * NB + 3 * NB) * 8;
+
+// W block layout ("k-group major", the A-operand layout of trsm_kernel):  B[kk][q] = (U^{-T})[kk][q] = W[q][kk]
+// sits at  (q / 4) * 512 + kk * 4 + q % 4.
+__device__ __forceinline__ int wg_index(int kk, int q) { return (q >> 2) * (NB * 4) + kk * 4 + (q & 3); }
+
+// ------------------------------------------------------------------------------------------------------------
+// diagonal block
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __restrict__ Wg, int* __restrict__ info)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* S = reinterpret_cast<double*>(smem_raw);          // U_kk (upper, diagonal included), row length SLD
+    double* rowbuf = S + NB * SLD;                            // 2 x NB: the broadcast pivot row, double-buffered
+    double* dpiv = rowbuf + 2 * NB;                           // pivots d_j (= U_jj^2)
+    double* udiag = dpiv + NB;                                // U_jj
+    double* uinv = udiag + NB;                                // 1 / U_jj
+    const int t = threadIdx.x, tr = t >> 4, tc = t & 15;      // thread owns rows tr + 32 i, columns tc + 16 k (cyclic)
+
+    double a[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = tr + 32 * i, c = tc + 16 * k;
+            double v = (r == c) ? 1.0 : 0.0;                  // identity padding of a ragged last block
+            if (r < nb && c < nb) v = (c >= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0;
+            a[i][k] = v;
+        }
+
+    // ---- phase 1: right-looking elimination.  After step j, row j holds d_j^{1/2}-unscaled U: U[j][c] = a[j][c] / sqrt(d_j)
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+#pragma unroll 1
+        for (int jj = 0; jj < 32; ++jj) {
+            const int j = 32 * jb + jj;
+            double* buf = rowbuf + (j & 1) * NB;
+            if (tr == jj) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) buf[tc + 16 * k] = a[jb][k];
+            }
+            __syncthreads();
+            const double d = buf[j];
+            if (t == 0) {
+                dpiv[j] = d;
+                if (!(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);   // not positive definite (LAPACK info convention)
+            }
+            const double id = 1.0 / d;
+            // only entries that can lie on or above the diagonal are kept up to date: column group k reaches row group i
+            // iff k >= 2 i (columns tc + 16 k, rows tr + 32 i); rows <= j are final (i < jb)
+            double vc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k >= 2 * jb) vc[k] = buf[tc + 16 * k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < jb) continue;
+                const int r = tr + 32 * i;
+                const double vr = (r > j) ? buf[r] * id : 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k >= 2 * i) a[i][k] = fma(-vr, vc[k], a[i][k]);
+            }
+        }
+    }
+    __syncthreads();
+    if (t < NB) {
+        const double d = dpiv[t];
+        const double u = sqrt(d);
+        udiag[t] = u;
+        uinv[t] = 1.0 / u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = tr + 32 * i, c = tc + 16 * k;
+            if (c >= r) {
+                const double u = (c == r) ? udiag[r] : a[i][k] * uinv[r];
+                S[r * SLD + c] = u;
+                if (c < nb) A[(size_t)(k0 + r) * lda + k0 + c] = u;       // c >= r, so r < nb as well
+            }
+        }
+    __syncthreads();
+
+    // ---- phase 2: B = U^{-T} by the same sweep applied to the identity:  B[j][:] /= U_jj;  B[r][:] -= U[j][r] B[j][:], r > j
+    double b[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[i][k] = (tr + 32 * i == tc + 16 * k) ? 1.0 : 0.0;
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+#pragma unroll 1
+        for (int jj = 0; jj < 32; ++jj) {
+            const int j = 32 * jb + jj;
+            double* buf = rowbuf + (j & 1) * NB;
+            if (tr == jj) {
+                const double s = uinv[j];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k <= 2 * jb + 1) { b[jb][k] *= s; buf[tc + 16 * k] = b[jb][k]; }
+            }
+            __syncthreads();
+            double vc[8];                                      // row j of B vanishes right of column j: k <= 2 jb + 1
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k <= 2 * jb + 1) vc[k] = buf[tc + 16 * k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < jb) continue;
+                const int r = tr + 32 * i;
+                const double ur = (r > j) ? S[j * SLD + r] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k <= 2 * jb + 1) b[i][k] = fma(-ur, vc[k], b[i][k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Wg[wg_index(tr + 32 * i, tc + 16 * k)] = b[i][k];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// row panel:  U[k0 + kk, j] = sum_q B[kk][q] A[k0 + q, j]   for the 64 columns j0 .. j0 + 63 of this CTA
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TRSM_THREADS = 256;
+constexpr int TRSM_SMEM = (WBLK + 32 * 64 * 4) * 8 + 16;
+
+__global__ void __launch_bounds__(TRSM_THREADS, 1)
+trsm_kernel(double* __restrict__ A, long long lda, long long n, int k0, const double* __restrict__ Wg, double* __restrict__ P,
+            int kg_stride, int g_off)         // P: panel-major with kg_stride k-groups per row; this panel fills groups g_off .. g_off + 31
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sW = reinterpret_cast<double*>(smem_raw);         // B[kk][q], k-group major (128 KB)
+    double* sB = sW + WBLK;                                   // A tile, [q / 4][j][q % 4] (64 KB)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32 * 64 * 4);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const long long s = (long long)k0 + NB;                   // first trailing column
+    const long long j0 = s + 64ll * blockIdx.x;
+
+    if (t == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, WBLK * 8);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bulk_g2s(sW + c * (WBLK / 4), Wg + c * (WBLK / 4), (WBLK / 4) * 8, bar);
+    }
+    {
+        const int j = t & 63;
+        const bool in = j0 + j < n;
+        for (int g = t >> 6; g < 32; g += 4) {
+            double v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = in ? A[(size_t)(k0 + 4 * g + e) * lda + j0 + j] : 0.0;
+            double2* dst = reinterpret_cast<double2*>(sB + g * 256 + j * 4);
+            dst[0] = make_double2(v[0], v[1]);
+            dst[1] = make_double2(v[2], v[3]);
+        }
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    // warp w: rows kk = 16 w .. 16 w + 15 (2 fragments) x 64 columns (8 fragments); B is lower triangular: q <= kk
+    double acc[2][8][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    const int frag = (lane >> 2) * 4 + (lane & 3);
+    const int g_end = 4 * warp + 4;
+    for (int g = 0; g < g_end; ++g) {
+        double af[2], bf[8];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) af[mi] = sW[g * (NB * 4) + (16 * warp + 8 * mi) * 4 + frag];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) bf[ni] = sB[g * 256 + (8 * ni) * 4 + frag];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+    }
+    const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((j0 & 1) == 0);
+    double* Pp = P + ((size_t)blockIdx.x * kg_stride + g_off) * 256;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+            const int kk = 16 * warp + 8 * mi + (lane >> 2), j = 8 * ni + 2 * (lane & 3);
+            const double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
+            Pp[(kk >> 2) * 256 + j * 4 + (kk & 3)] = v0;          // zero beyond column n (the A tile was zero-filled)
+            Pp[(kk >> 2) * 256 + (j + 1) * 4 + (kk & 3)] = v1;
+            double* dst = A + (size_t)(k0 + kk) * lda + j0 + j;
+            if (j0 + j + 1 < n && vec_ok) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            else {
+                if (j0 + j < n) dst[0] = v0;
+                if (j0 + j + 1 < n) dst[1] = v1;
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// triangular solves with one right-hand side, one launch per block
+// ------------------------------------------------------------------------------------------------------------
+// forward (U^T y = b):  y_k = B r_k;  r_j -= U[k-rows, j]^T y_k for the columns j behind the block.
+// CTA = 64 columns x 4 slices of the block's rows (32 each), reduced through shared memory.
+__global__ void __launch_bounds__(256)
+fwd_step_kernel(const double* __restrict__ U, long long lda, long long n, int k0, int nb, const double* __restrict__ Wg,
+                double* __restrict__ r, double* __restrict__ y)
+{
+    __shared__ double rk[NB], z[NB], part[4][64];
+    const int t = threadIdx.x;
+    if (t < NB) rk[t] = t < nb ? r[k0 + t] : 0.0;
+    __syncthreads();
+    if (t < NB) {
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int g = 0; g <= (t >> 2); ++g) {
+            const double2* w = reinterpret_cast<const double2*>(Wg + g * (NB * 4) + t * 4);
+            const double2 w0 = w[0], w1 = w[1];
+            acc0 = fma(w0.x, rk[4 * g], acc0); acc1 = fma(w0.y, rk[4 * g + 1], acc1);
+            acc0 = fma(w1.x, rk[4 * g + 2], acc0); acc1 = fma(w1.y, rk[4 * g + 3], acc1);
+        }
+        z[t] = acc0 + acc1;
+        if (blockIdx.x == 0 && t < nb) y[k0 + t] = acc0 + acc1;
+    }
+    __syncthreads();
+    const int tx = t & 63, ty = t >> 6;
+    const long long j = (long long)k0 + nb + 64ll * blockIdx.x + tx;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (j < n) {
+        const double* col = U + (size_t)(k0 + 32 * ty) * lda + j;
+        const double* zz = z + 32 * ty;
+        const int lim = min(32, nb - 32 * ty);
+        int kk = 0;
+#pragma unroll 2
+        for (; kk + 3 < lim; kk += 4) {
+            a0 = fma(col[(size_t)kk * lda], zz[kk], a0);
+            a1 = fma(col[(size_t)(kk + 1) * lda], zz[kk + 1], a1);
+            a2 = fma(col[(size_t)(kk + 2) * lda], zz[kk + 2], a2);
+            a3 = fma(col[(size_t)(kk + 3) * lda], zz[kk + 3], a3);
+        }
+        for (; kk < lim; ++kk) a0 = fma(col[(size_t)kk * lda], zz[kk], a0);
+    }
+    part[ty][tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && j < n) r[j] -= (part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx]);
+}
+
+// backward (U x = y):  x_k = B^T r_k;  r_i -= U[i, k-cols] x_k for the rows i above the block.
+// CTA = 64 rows, 4 threads per row (32 contiguous doubles each), reduced by shuffles.
+__global__ void __launch_bounds__(256)
+bwd_step_kernel(const double* __restrict__ U, long long lda, long long n, int k0, int nb, const double* __restrict__ Wg,
+                double* __restrict__ r, double* __restrict__ x)
+{
+    __shared__ double rk[NB], z[NB];
+    const int t = threadIdx.x;
+    if (t < NB) rk[t] = t < nb ? r[k0 + t] : 0.0;
+    __syncthreads();
+    if (t < NB) {
+        double acc0 = 0.0, acc1 = 0.0;                      // z[q] = sum_{kk >= q} B[kk][q] r[kk]
+        const double* w = Wg + (t >> 2) * (NB * 4) + (t & 3);
+        int kk = t;
+        for (; kk + 1 < NB; kk += 2) { acc0 = fma(w[kk * 4], rk[kk], acc0); acc1 = fma(w[kk * 4 + 4], rk[kk + 1], acc1); }
+        if (kk < NB) acc0 = fma(w[kk * 4], rk[kk], acc0);
+        z[t] = acc0 + acc1;
+        if (blockIdx.x == 0 && t < nb) x[k0 + t] = acc0 + acc1;
+    }
+    __syncthreads();
+    const int sub = t & 3;
+    const long long i = 64ll * blockIdx.x + (t >> 2);
+    double acc0 = 0.0, acc1 = 0.0;
+    if (i < k0) {
+        const double* row = U + (size_t)i * lda + k0 + 32 * sub;
+        const int lim = min(32, nb - 32 * sub);
+#pragma unroll 8
+        for (int q = 0; q + 1 < lim; q += 2) {
+            acc0 = fma(row[q], z[32 * sub + q], acc0);
+            acc1 = fma(row[q + 1], z[32 * sub + q + 1], acc1);
+        }
+        if (lim > 0 && (lim & 1)) acc0 = fma(row[lim - 1], z[32 * sub + lim - 1], acc0);
+    }
+    double tot = acc0 + acc1;
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+    if (sub == 0 && i < k0) r[i] -= tot;
+}
+
+static inline long long n_blocks(long long n) { return (n + NB - 1) / NB; }
+static inline long long panel_doubles(long long n) { return (((n + 127) / 128) * 128 + 128) * (2 * NB); }
+
+}  // namespace chol
+}  // namespace lsk
+
+extern "C" long long lsk_potrf_work_doubles(long long n) {
+    using namespace lsk::chol;
+    if (n < 0) return LSK_ESIZE;
+    return n_blocks(n) * WBLK + panel_doubles(n);
+}
+
+// Two 128-column panel steps per trailing update, so that the update runs with K = 256 (half the read-modify-write traffic
+// and half the per-tile overhead of K = 128):
+//   diag(k0); trsm(k0) -> P[:, 0:128];  strip: rows [k0+128, k0+256) x cols [k0+128, n) -= P1^T P1 (K = 128);
+//   diag(k0+128); trsm(k0+128) -> P[:, 128:256];  trailing rows/cols [k0+256, n) -= [P1 P2]^T [P1 P2] (K = 256).
+extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_, void* info_dev, void* stream) {
+    using namespace lsk;
+    using namespace lsk::chol;
+    if (!A_ || !work_ || !info_dev) return LSK_EARG;
+    if (n < 0 || lda < n || n > 0x7fffffffLL) return LSK_ESIZE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double* A = static_cast<double*>(A_);
+    double* W = static_cast<double*>(work_);
+    double* P = W + n_blocks(n) * WBLK;
+    int* info = static_cast<int*>(info_dev);
+    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    if (n == 0) return 0;
+    e = cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+
+    constexpr int KG2 = 2 * NB / 4;                      // k-groups per row of the two-panel operand
+    LskEpilogue ep = {};
+    ep.kind = LSK_EPI_SYRK; ep.nforms = 1; ep.nvars = 1; ep.nterms = 1;
+    ep.out_layout = LSK_OUT_ROW_MAJOR;
+    ep.scale = -1.0;
+    ep.group_begin[0] = 0;
+
+    for (long long k0 = 0, blk = 0; k0 < n; k0 += 2 * NB, blk += 2) {
+        // ---- first panel
+        const int nb1 = (int)((n - k0) < NB ? (n - k0) : NB);
+        diag_kernel<<<1, 512, DIAG_SMEM, st>>>(A, lda, (int)k0, nb1, W + blk * WBLK, info);
+        const long long s1 = k0 + NB, m1 = n - s1;
+        if (m1 <= 0) break;
+        trsm_kernel<<<(unsigned)(((m1 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, (int)k0, W + blk * WBLK, P, KG2, 0);
+        // ---- strip of the next 128 rows (general accumulate, K = 128)
+        const long long strip = m1 < NB ? m1 : NB;
+        ep.group_end[0] = NB / 4;
+        ep.reserved = 0;
+        int rc = lsk_pairwise_poly(P, P, strip, m1, KG2, &ep, A + s1 * lda + s1, lda, stream);
+        if (rc != 0) return rc;
+        // ---- second panel
+        diag_kernel<<<1, 512, DIAG_SMEM, st>>>(A, lda, (int)s1, (int)strip, W + (blk + 1) * WBLK, info);
+        const long long s2 = s1 + NB, m2 = n - s2;
+        if (m2 <= 0) break;
+        double* P2 = P + 2ll * KG2 * 256;                // operand rows are relative to s2: two 64-row panels further
+        trsm_kernel<<<(unsigned)(((m2 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, (int)s1, W + (blk + 1) * WBLK, P2, KG2, NB / 4);
+        // ---- trailing update (upper triangle of tiles, K = 256)
+        ep.group_end[0] = KG2;
+        ep.reserved = 2;
+        rc = lsk_pairwise_poly(P2, P2, m2, m2, KG2, &ep, A + s2 * lda + s2, lda, stream);
+        if (rc != 0) return rc;
+    }
+    return (int)cudaGetLastError();
+}
+
+// which: 1 = forward only (U^T y = b), 2 = backward only (U x = b), 3 = both (U^T U x = b).  `b` is overwritten with the
+// solution; `tmp` is an n-double scratch vector.
+extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const void* work_, void* b_, void* tmp_, int which,
+                               void* stream) {
+    using namespace lsk::chol;
+    if (!U_ || !work_ || !b_ || !tmp_) return LSK_EARG;
+    if (n < 0 || lda < n || n > 0x7fffffffLL) return LSK_ESIZE;
+    if (which < 1 || which > 3) return LSK_EARG;
+    if (n == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double* U = static_cast<const double*>(U_);
+    const double* W = static_cast<const double*>(work_);
+    double* b = static_cast<double*>(b_);
+    double* tmp = static_cast<double*>(tmp_);
+    const long long nblk = n_blocks(n);
+    double* cur = b;      // residual vector that is consumed
+    double* oth = tmp;    // solution vector that is produced
+    if (which & 1) {
+        for (long long blk = 0; blk < nblk; ++blk) {
+            const long long k0 = blk * NB;
+            const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
+            const long long m = n - k0 - nb;
+            const unsigned grid = (unsigned)(m > 0 ? (m + 63) / 64 : 1);
+            fwd_step_kernel<<<grid, 256, 0, st>>>(U, lda, n, (int)k0, nb, W + blk * WBLK, cur, oth);
+        }
+        double* sw = cur; cur = oth; oth = sw;
+    }
+    if (which & 2) {
+        for (long long blk = nblk - 1; blk >= 0; --blk) {
+            const long long k0 = blk * NB;
+            const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
+            const unsigned grid = (unsigned)(k0 > 0 ? (k0 + 63) / 64 : 1);
+            bwd_step_kernel<<<grid, 256, 0, st>>>(U, lda, n, (int)k0, nb, W + blk * WBLK, cur, oth);
+        }
+        double* sw = cur; cur = oth; oth = sw;
+    }
+    if (cur != b) {
+        cudaError_t e = cudaMemcpyAsync(b, cur, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return (int)cudaGetLastError();
+}

@@ -230,17 +230,24 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
     constexpr bool sym = SYM;        // compile-time: the general kernel carries none of the triangular-schedule code
     const long long n_tiles = sym ? (long long)row_tiles * col_panels - (long long)row_tiles * (row_tiles - 1)
                                   : (long long)row_tiles * col_panels;
-    // tile index -> (row tile, column panel); loop-free (it is also evaluated under the producer's divergent branch)
+    // tile index -> (row tile, column panel); loop-free (it is also evaluated under the producer's divergent branch, once
+    // per pipeline chunk) and integer-only.  Triangular schedule: row tile r owns the col_panels - 2 r tiles that reach the
+    // diagonal or lie right of it; rows r and row_tiles - 1 - r together always own W = 2 col_panels - 2 (row_tiles - 1)
+    // tiles, so a tile index splits into (pair, offset) with one division.
+    const int pair_w = 2 * col_panels - 2 * (row_tiles - 1);
+    const bool small_index = n_tiles <= 0x7fffffffLL;
     auto tile_coords = [&](long long t, int& pr, int& pc) {
-        if constexpr (!SYM) { pr = (int)(t / col_panels); pc = (int)(t % col_panels); return; }
-        // row tile r owns col_panels - 2 r tiles; S(r) = r * col_panels - r (r - 1) tiles precede it
-        const double c1 = (double)col_panels + 1.0;
-        int r = (int)(0.5 * (c1 - sqrt(fmax(c1 * c1 - 4.0 * (double)t, 0.0))));
-        r = max(0, min(r, row_tiles - 1));
-        if ((long long)r * col_panels - (long long)r * (r - 1) > t) --r;
-        if (r + 1 < row_tiles && (long long)(r + 1) * col_panels - (long long)(r + 1) * r <= t) ++r;
-        pr = r;
-        pc = 2 * r + (int)(t - ((long long)r * col_panels - (long long)r * (r - 1)));
+        if constexpr (!SYM) {
+            if (small_index) { const unsigned q = (unsigned)t / (unsigned)col_panels; pr = (int)q; pc = (int)((unsigned)t - q * (unsigned)col_panels); }
+            else { pr = (int)(t / col_panels); pc = (int)(t % col_panels); }
+            return;
+        }
+        int pair, off;
+        if (small_index) { const unsigned q = (unsigned)t / (unsigned)pair_w; pair = (int)q; off = (int)((unsigned)t - q * (unsigned)pair_w); }
+        else { pair = (int)(t / pair_w); off = (int)(t % pair_w); }
+        const int first = col_panels - 2 * pair;
+        if (off < first) { pr = pair; pc = 2 * pair + off; }
+        else { pr = row_tiles - 1 - pair; pc = 2 * pr + (off - first); }
     };
 
     // producer state in shared memory: [0] next chunk (CTA-local sequence number) to be issued, [1] chunks per tile,
@@ -354,6 +361,29 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
             for (int m = 0; m < MT; ++m)
 #pragma unroll
                 for (int n = 0; n < 2; ++n) { acc[f][m][n][0] = 0.0; acc[f][m][n][1] = 0.0; }
+        // SYRK: the entries this thread will update are requested now and consumed after the DMMA phase, so the
+        // read half of the read-modify-write hides behind the tile's tensor-core work
+        double prev[EPI == LSK_EPI_SYRK ? MT : 1][2][2];
+        if constexpr (EPI == LSK_EPI_SYRK) {
+            const int r_base = pr * BMT + wr * (8 * MT) + (lane >> 2), c_base = pc * BN + wc * 16 + 2 * (lane & 3);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    const int row = r_base + m * 8, col = c_base + n * 8;
+                    prev[m][n][0] = 0.0; prev[m][n][1] = 0.0;
+                    if (row < n_rows && col < n_cols) {
+                        const double* src = out + (size_t)row * ld_out + col;
+                        if (vec_ok && col + 1 < n_cols) {
+                            const double2 v = *reinterpret_cast<const double2*>(src);
+                            prev[m][n][0] = v.x; prev[m][n][1] = v.y;
+                        } else {
+                            prev[m][n][0] = src[0];
+                            if (col + 1 < n_cols) prev[m][n][1] = src[1];
+                        }
+                    }
+                }
+        }
 
         // ---- bilinear forms on the tensor-core path: every form is cut into chunks of <= KG_PER_STAGE k-groups,
         //      one pipeline stage each; inside a stage all offsets are immediates ----
@@ -425,7 +455,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 dst = out + (size_t)row * ld_out + c;
                 pair_ok = vec_ok && ((c & 1) == 0);
             }
-            if constexpr (SYM) {          // mirror (row-major only): entries strictly above the diagonal
+            if constexpr (SYM && EPI != LSK_EPI_SYRK) {          // mirror (row-major only): entries strictly above the diagonal
                 if (col > row) st_cs_f64(out + (size_t)col * ld_out + row, r0);
                 if (col + 1 > row && col + 1 < n_cols) st_cs_f64(out + (size_t)(col + 1) * ld_out + row, r1);
             }
@@ -454,7 +484,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                 for (int f = 0; f < NF; ++f) u[f] = acc[f][2 * h + ml][n][i];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    if constexpr (EPI == LSK_EPI_LINEAR) var[v][e] = u[0];
+                    if constexpr (EPI == LSK_EPI_LINEAR || EPI == LSK_EPI_SYRK) var[v][e] = u[0];
                     else {
                         // forms flagged in bits 8.. of `reserved` enter squared (sign-ambiguous spinor form)
                         double x = p.aff[v][0];
@@ -488,7 +518,7 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                     if constexpr (GEN > 0) gen_epilogue<GEN, R, NV>(p, var, res);
                     else epi_tape<R, NV>(p.coef, p.nterms, var, res);
                 }
-                else if constexpr (EPI == LSK_EPI_LINEAR) {
+                else if constexpr (EPI == LSK_EPI_LINEAR || EPI == LSK_EPI_SYRK) {
 #pragma unroll
                     for (int e = 0; e < R; ++e) res[e] = var[0][e];
                 } else {
@@ -503,7 +533,10 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 #pragma unroll
                 for (int e = 0; e < R; e += 2) {
                     const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
-                    store_pair(row0 + m * 8, col0 + n * 8, 0, p.scale * res[e], p.scale * res[e + 1]);
+                    if constexpr (EPI == LSK_EPI_SYRK)
+                        store_pair(row0 + m * 8, col0 + n * 8, 0, fma(p.scale, res[e], prev[m][n][0]), fma(p.scale, res[e + 1], prev[m][n][1]));
+                    else
+                        store_pair(row0 + m * 8, col0 + n * 8, 0, p.scale * res[e], p.scale * res[e + 1]);
                 }
             }
         }
@@ -548,7 +581,9 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.group_begin[f] < 0 || p.group_end[f] > kg_total || p.group_begin[f] >= p.group_end[f]) return LSK_EARG;
     for (int f = 1; f < p.nforms; ++f)
         if (p.group_begin[f] != p.group_end[f - 1]) return LSK_EARG;   // forms tile the k range in order
-    if (p.group_begin[0] != 0 || p.group_end[p.nforms - 1] != kg_total) return LSK_EARG;
+    // kg_total is the operand row stride; the forms may stop short of it (SYRK on the first half of a two-panel operand)
+    if (p.group_begin[0] != 0 || p.group_end[p.nforms - 1] > kg_total) return LSK_EARG;
+    if (p.kind != LSK_EPI_SYRK && p.group_end[p.nforms - 1] != kg_total) return LSK_EARG;
 
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -614,6 +649,9 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
     case LSK_EPI_LINEAR:
         if (p.nforms == 1 && p.nvars == 1) LSK_GO_SYM(LSK_EPI_LINEAR, 1, 1, 1);
         return LSK_EARG;
+    case LSK_EPI_SYRK:
+        if (p.nforms != 1 || p.nvars != 1 || p.out_layout != LSK_OUT_ROW_MAJOR) return LSK_EARG;
+        LSK_GO_SYM(LSK_EPI_SYRK, 1, 1, 1);
     case LSK_EPI_SPARSE:
     case LSK_EPI_FEAT_SPARSE:
         return LSK_EUNSUPPORTED;        // monomial-list encoding: only lsk_homog_pairs reads it

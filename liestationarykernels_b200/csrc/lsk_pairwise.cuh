@@ -20,6 +20,8 @@
 
 #define LSK_EPI_HORNER      8   // any:     nested Horner over a tape of (coefficient, op) steps (lsk_pairwise.cu epi_tape)
 #define LSK_EPI_FEAT_HORNER 9   // per-irrep outputs, any rank: row l is a tape of row_len[l] steps
+#define LSK_EPI_SYRK       10   // out += scale * form_0 on the tiles that reach the diagonal or lie above it, nothing mirrored
+                                // (trailing update of the blocked Cholesky, lsk_cholesky.cu; square row-major output)
 
 #define LSK_OUT_ROW_MAJOR   0   // out[i * ld_out + j]
 #define LSK_OUT_PANEL_MAJOR 1   // operand layout of this kernel: [i / 64][j / 4][i % 64][j % 4], out_kg k-groups per row

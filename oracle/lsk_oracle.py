@@ -554,3 +554,40 @@ def rff_sample(space, measure, lmd, shift, w_re, w_im, x, normalizer):
     s_re = torch.einsum("nm,m->n", f.real, w_re)
     s_im = torch.einsum("nm,m->n", f.imag, w_im)
     return (s_re - s_im) / math.sqrt(normalizer)
+
+
+# =====================================================================================================================
+# GP regression step (examples/gpr_model.py:12-92, examples/gpr_experiments.py:75-87)
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference delegates this to gpytorch ~1.7 (pyproject.toml:16-23; absent from the image, PARITY UNPINNED for this
+# block): ExactGP + GaussianLikelihood + ExactMarginalLogLikelihood.  Its published algorithm for dense covariances of
+# this size is a Cholesky factorisation (psd_safe_cholesky -> LAPACK dpotrf) followed by triangular solves:
+#     log p(y) = -1/2 ( r^T S^{-1} r + log det S + n log 2 pi ),  S = K + 1e-6 I + noise I,  r = y - mean,
+#     mll = log p(y) / n                                   (ExactMarginalLogLikelihood divides by the number of data)
+#     posterior: mean* = m + K*^T S^{-1} r,  cov* = K** + 1e-6 I - K*^T S^{-1} K*
+#     noise = softplus(raw_noise) + 1e-4   (GaussianLikelihood's default GreaterThan(1e-4) constraint, raw_noise = 0)
+# restated here with torch CPU / LAPACK.
+# =====================================================================================================================
+def gp_noise(raw_noise):
+    return torch.nn.functional.softplus(raw_noise) + 1e-4
+
+
+def gp_log_marginal(K, noise, mean, y):
+    """log p(y) / n for y ~ N(mean, K + 1e-6 I + noise I); differentiable (torch autograd through LAPACK)."""
+    n = y.shape[0]
+    S = K + (1e-6 + noise) * torch.eye(n, dtype=torch.float64)
+    L = torch.linalg.cholesky(S)
+    r = (y - mean)[:, None]
+    alpha = torch.cholesky_solve(r, L)
+    logdet = 2.0 * torch.log(torch.diagonal(L)).sum()
+    return -0.5 * ((r * alpha).sum() + logdet + n * math.log(2.0 * math.pi)) / n
+
+
+def gp_posterior(K, K_star, K_ss, noise, mean, y):
+    """Posterior mean and covariance at the test points (K_star: [n, n*], K_ss: [n*, n*])."""
+    n = y.shape[0]
+    S = K + (1e-6 + noise) * torch.eye(n, dtype=torch.float64)
+    L = torch.linalg.cholesky(S)
+    alpha = torch.cholesky_solve((y - mean)[:, None], L)[:, 0]
+    v = torch.linalg.solve_triangular(L, K_star, upper=False)
+    return mean + K_star.T @ alpha, K_ss + 1e-6 * torch.eye(K_ss.shape[0], dtype=torch.float64) - v.T @ v

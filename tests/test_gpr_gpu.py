@@ -1,0 +1,209 @@
+"""GP regression step on the covariance: the blocked fp64 Cholesky / triangular solves behind the C ABI
+(`lsk_potrf_upper`, `lsk_potrs_upper`) against LAPACK on the CPU, and the marginal likelihood, its gradients and the
+posterior of `liestationarykernels_b200.gpr` against the oracle's restatement of the gpytorch path.
+
+Tolerances (float64): factor and solves <= 1e-10 relative (matrices with condition number <= 1e5), log-likelihood and
+gradients <= 1e-9 relative."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _covariance(n, noise, seed=0):
+    """a real covariance matrix of the hot path: SO(3) heat kernel at n Haar points + noise"""
+    from liestationarykernels_b200.spaces import SO
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import SqExpSpectralMeasure
+    torch.manual_seed(seed)
+    space = SO(3, order=20)
+    kern = EigenbasisSumKernel(SqExpSpectralMeasure(3, 0.7), space).eval()
+    with torch.no_grad():
+        k = kern(space.rand(n))
+    return k + noise * torch.eye(n, dtype=torch.float64, device="cuda")
+
+
+@pytest.mark.parametrize("n", [1, 3, 64, 127, 128, 129, 255, 256, 257, 300, 385, 777, 1025])
+def test_cholesky_matches_lapack(n):
+    from liestationarykernels_b200.linalg import CholeskyFactor
+    a = _covariance(n, 1e-2, seed=n)
+    ref = torch.linalg.cholesky(a.cpu())
+    f = CholeskyFactor(a)
+    assert f.info == 0
+    assert (f.L.cpu() - ref).abs().max().item() <= 1e-10 * ref.abs().max().item()
+    assert torch.equal(f.U, f.L.mT)
+    torch.manual_seed(1)
+    b = torch.randn(n, dtype=torch.float64)
+    x_ref = torch.cholesky_solve(b[:, None], ref)[:, 0]
+    y_ref = torch.linalg.solve_triangular(ref, b[:, None], upper=False)[:, 0]
+    z_ref = torch.linalg.solve_triangular(ref.mT, b[:, None], upper=True)[:, 0]
+    for got, want in ((f.solve(b.cuda()), x_ref), (f.solve_lower(b.cuda()), y_ref), (f.solve_upper(b.cuda()), z_ref)):
+        assert (got.cpu() - want).abs().max().item() <= 1e-10 * want.abs().max().item()
+    assert abs(f.logdet().item() - 2 * torch.log(torch.diagonal(ref)).sum().item()) <= 1e-10 * max(1.0, n)
+
+
+def test_cholesky_multiple_right_hand_sides_and_strided_input():
+    from liestationarykernels_b200.linalg import CholeskyFactor, cholesky
+    a = _covariance(300, 1e-2)
+    big = torch.zeros(300, 340, dtype=torch.float64, device="cuda")
+    big[:, :300] = a
+    view = big[:, :300]                              # row stride 340: factorised from a copy, the input is untouched
+    f = CholeskyFactor(view)
+    assert torch.equal(big[:, :300], a)
+    b = torch.randn(300, 5, dtype=torch.float64, device="cuda")
+    x = f.solve(b)
+    assert ((a @ x - b).abs().max() / b.abs().max()).item() < 1e-10
+    L = cholesky(a)
+    assert (L @ L.mT - a).abs().max().item() < 1e-12
+    assert (cholesky(a, upper=True) - L.mT).abs().max().item() == 0.0
+
+
+def test_cholesky_in_place_with_leading_dimension():
+    """C ABI with lda > n: the factor lands in the upper triangle of the caller's buffer, columns beyond n are untouched"""
+    import ctypes
+    from liestationarykernels_b200 import _lib
+    lib = _lib.load()
+    n, lda = 333, 352
+    a = _covariance(n, 1e-2)
+    buf = torch.full((n, lda), 7.0, dtype=torch.float64, device="cuda")
+    buf[:, :n] = a
+    work = torch.empty(lib.lsk_potrf_work_doubles(n), dtype=torch.float64, device="cuda")
+    info = torch.ones(1, dtype=torch.int32, device="cuda")
+    assert lib.lsk_potrf_upper(_lib.ptr(buf), n, lda, _lib.ptr(work), _lib.ptr(info), _lib.stream_ptr()) == 0
+    assert info.item() == 0
+    ref = torch.linalg.cholesky(a.cpu())
+    assert (torch.triu(buf[:, :n]).cpu() - ref.mT).abs().max().item() <= 1e-10 * ref.abs().max().item()
+    assert torch.all(buf[:, n:] == 7.0)
+    # argument errors
+    assert lib.lsk_potrf_upper(_lib.ptr(buf), n, n - 1, _lib.ptr(work), _lib.ptr(info), _lib.stream_ptr()) == -2
+    assert lib.lsk_potrf_upper(None, n, lda, _lib.ptr(work), _lib.ptr(info), _lib.stream_ptr()) == -1
+    assert lib.lsk_potrs_upper(_lib.ptr(buf), n, lda, _lib.ptr(work), _lib.ptr(work), _lib.ptr(work), 0, _lib.stream_ptr()) == -1
+
+
+def test_not_positive_definite_reports_lapack_info():
+    from liestationarykernels_b200.linalg import CholeskyFactor, NotPositiveDefiniteError
+    a = _covariance(300, 1e-2)
+    a[200, 200] = -1.0
+    assert CholeskyFactor(a, check=False).info == 201
+    with pytest.raises(NotPositiveDefiniteError):
+        CholeskyFactor(a)
+    empty = CholeskyFactor(torch.zeros(0, 0, dtype=torch.float64, device="cuda"))
+    assert empty.info == 0 and empty.L.shape == (0, 0)
+
+
+def test_large_factorisation_residual():
+    """size-independent property at a size LAPACK would take too long for: ||U^T U - A|| and A x = b residuals"""
+    from liestationarykernels_b200.linalg import CholeskyFactor
+    n = 5000
+    a = _covariance(n, 1e-1)
+    f = CholeskyFactor(a)
+    u = f.U
+    assert ((u.mT @ u - a).abs().max() / a.abs().max()).item() < 1e-13
+    b = torch.randn(n, dtype=torch.float64, device="cuda")
+    assert ((a @ f.solve(b) - b).norm() / b.norm()).item() < 1e-12
+
+
+def test_log_prob_and_gradients_match_lapack_autograd():
+    from liestationarykernels_b200.gpr import MultivariateNormal
+    import lsk_oracle as orc
+    torch.manual_seed(3)
+    n = 200
+    a = _covariance(n, 5e-2).cpu()
+    y = torch.randn(n, dtype=torch.float64)
+    m = torch.full((n,), 0.3, dtype=torch.float64)
+    a_ref, m_ref = a.clone().requires_grad_(True), m.clone().requires_grad_(True)
+    want = orc.gp_log_marginal(a_ref, torch.tensor(-1e-6, dtype=torch.float64), m_ref, y) * n
+    want.backward()
+    a_g, m_g = a.cuda().requires_grad_(True), m.cuda().requires_grad_(True)
+    got = MultivariateNormal(m_g, a_g).log_prob(y.cuda())
+    got.backward()
+    assert abs(got.item() - want.item()) <= 1e-10 * abs(want.item())
+    # autograd through LAPACK's potrf gives the gradient of the lower triangle only; symmetrise both
+    g_ref = 0.5 * (a_ref.grad + a_ref.grad.T)
+    g_got = 0.5 * (a_g.grad + a_g.grad.mT).cpu()
+    assert (g_got - g_ref).abs().max().item() <= 1e-9 * g_ref.abs().max().item()
+    assert (m_g.grad.cpu() - m_ref.grad).abs().max().item() <= 1e-9 * m_ref.grad.abs().max().item()
+
+
+def test_gp_training_step_matches_oracle():
+    """one evaluation of the reference's training loss (examples/gpr_model.py:59-66) and its gradients with respect to
+    lengthscale, variance, noise and mean: ours on the GPU against the oracle kernel + LAPACK differentiated on the CPU"""
+    import lsk_oracle as orc
+    from liestationarykernels_b200 import gpr
+    from liestationarykernels_b200.spaces import SO
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(5)
+    og = orc.Group("SO", 3, 10)
+    n = 40
+    x = og.rand(n)
+    y = torch.randn(n, dtype=torch.float64)
+    # ---- oracle
+    om = orc.Measure("matern", og.dim, 0.8, 1.5, 1.7)
+    om.lengthscale.requires_grad_(True)
+    om.variance.requires_grad_(True)
+    raw_noise = torch.zeros(1, dtype=torch.float64, requires_grad=True)
+    const = torch.zeros(1, dtype=torch.float64, requires_grad=True)
+    emb = og.pairwise_embed(x, x)
+    cov = torch.zeros(n, n, dtype=torch.float64)
+    norm = torch.zeros((), dtype=torch.float64)
+    for irrep in og.irreps:
+        cov = cov + om(irrep[2]) * og.phase_function(irrep, emb).view(n, n).real
+        norm = norm + om(irrep[2])[0] * irrep[1] ** 2
+    k_ref = torch.abs(om.variance[0]) * cov / norm
+    loss_ref = -orc.gp_log_marginal(k_ref, orc.gp_noise(raw_noise)[0], const.expand(n), y)
+    loss_ref.backward()
+    # ---- ours
+    space = SO(3, order=10)
+    meas = MaternSpectralMeasure(og.dim, 0.8, 1.5, 1.7)
+    kern = EigenbasisSumKernel(meas, space)
+    lik = gpr.GaussianLikelihood(device="cuda")
+    tx = x.cuda().reshape(n, -1)
+    model = gpr.ExactGPModel(tx, y.cuda(), lik, kern, space, point_shape=(3, 3))
+    model.train()
+    loss = -gpr.ExactMarginalLogLikelihood(lik, model)(model(tx), y.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-10 * abs(loss_ref.item())
+    pairs = ((meas.lengthscale.grad, om.lengthscale.grad), (meas.variance.grad, om.variance.grad),
+             (lik.raw_noise.grad, raw_noise.grad), (model.mean_module.constant.grad, const.grad))
+    for ours, ref in pairs:
+        assert ours is not None
+        assert abs(ours.item() - ref.item()) <= 1e-9 * max(1e-3, abs(ref.item())), (ours.item(), ref.item())
+
+
+def test_gp_posterior_and_training_loop():
+    """train() lowers the loss; the eval-mode posterior equals the oracle's LAPACK posterior for the trained parameters"""
+    import lsk_oracle as orc
+    from liestationarykernels_b200 import gpr
+    from liestationarykernels_b200.spaces import SO
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    from liestationarykernels_b200.prior_approximation import RandomPhaseApproximation
+    torch.manual_seed(7)
+    space = SO(3, order=10)
+    f = RandomPhaseApproximation(EigenbasisSumKernel(MaternSpectralMeasure(3, 1.0, 2.5, 4.0), space), phase_order=200)
+    n_train, n_test = 200, 50
+    train_x, test_x = space.rand(n_train), space.rand(n_test)
+    with torch.no_grad():
+        train_y, test_y = f(train_x), f(test_x)
+    meas = MaternSpectralMeasure(3, 1.0, 1.5)
+    kern = EigenbasisSumKernel(meas, space)
+    lik = gpr.GaussianLikelihood(device="cuda")
+    model = gpr.ExactGPModel(train_x.reshape(n_train, -1), train_y, lik, kern, space, point_shape=(3, 3))
+    losses = gpr.train(model, train_x.reshape(n_train, -1), train_y, training_iter=30, lr_scheduler_step=15, lr=0.1, verbose=False)
+    assert losses[-1] < losses[0]
+    model.eval()
+    kern.eval()
+    with torch.no_grad():
+        pred = model(test_x.reshape(n_test, -1))
+        k = kern(train_x).cpu()
+        ks = kern(train_x, test_x).cpu()
+        kss = kern(test_x).cpu()
+    mean_ref, cov_ref = orc.gp_posterior(k, ks, kss, lik.noise.detach().cpu()[0], model.mean_module.constant.detach().cpu(),
+                                         train_y.cpu())
+    assert (pred.mean.cpu() - mean_ref).abs().max().item() <= 1e-9 * max(1.0, mean_ref.abs().max().item())
+    assert (pred.covariance_matrix.cpu() - cov_ref).abs().max().item() <= 1e-9 * max(1.0, cov_ref.abs().max().item())
+    mse = ((pred.mean - test_y) ** 2).mean().item()
+    assert mse < test_y.var(unbiased=False).item()          # the fitted GP beats the constant predictor
+    test_ll = gpr.ExactMarginalLogLikelihood(lik, model)(pred, test_y).item()
+    assert test_ll == test_ll
