@@ -7,6 +7,6 @@ from liestationarykernels_b200 import prior_approximation, space, spaces, spectr
 
 for _name in ("prior_approximation", "space", "spaces", "spectral_kernel", "spectral_measure", "utils"):
     _sys.modules[__name__ + "." + _name] = getattr(_impl, _name) if hasattr(_impl, _name) else _sys.modules["liestationarykernels_b200." + _name]
-for _sub in ("so", "su", "stiefel", "grassmannian", "hyperbolic", "spd", "torus"):
+for _sub in ("so", "su", "stiefel", "grassmannian", "hyperbolic", "spd", "torus", "sphere"):
     import importlib as _il
     _sys.modules[__name__ + ".spaces." + _sub] = _il.import_module("liestationarykernels_b200.spaces." + _sub)

@@ -143,13 +143,21 @@ def class_features(plan: GroupPlan, x: torch.Tensor, phases: torch.Tensor, row_s
     if panel and P % 4:
         # irrep column blocks must start on a k-group boundary in the panel layout: go through the dense form
         return PanelMatrix.from_dense(class_features(plan, x, phases, row_scales, panel=False))
-    ea = embed(plan, x, "a")
-    eb = embed(plan, phases, "b")
+    return features_from_operands(plan, embed(plan, x, "a"), embed(plan, phases, "b"), N, P, row_scales, panel, x.device)
+
+
+def features_from_operands(plan, ea: torch.Tensor, eb: torch.Tensor, N: int, P: int, row_scales, panel: bool, device):
+    """The per-irrep feature launches of `class_features` on ready panel-major operands (`plan` supplies the bilinear
+    forms and the per-irrep polynomials: a classfn.GroupPlan or the zonal plan of spaces/sphere.py)."""
+    L = len(plan.irreps)
+    if panel and P % 4:
+        dense = features_from_operands(plan, ea, eb, N, P, row_scales, False, device)
+        return PanelMatrix.from_dense(dense)
     if panel:
-        target = PanelMatrix(N, L * P, x.device)
+        target = PanelMatrix(N, L * P, device)
         out = target.buf
     else:
-        target = torch.zeros((N, L * P), dtype=F64, device=x.device)
+        target = torch.zeros((N, L * P), dtype=F64, device=device)
         out = target
     for ep, col_shift in plan.feature_epilogues(row_scales, P):
         if panel:

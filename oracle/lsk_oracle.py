@@ -337,6 +337,80 @@ class Torus:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# spaces/sphere.py — S^n and RP^n with zonal (Gegenbauer) phase functions
+# ----------------------------------------------------------------------------------------------------------
+class Sphere:
+    """sphere.py:17-57 (Sphere) and :60-108 (ProjectiveSpace: even degrees only).  irreps = (degree, dimension, eigenvalue).
+    The dimension comes from the absent `spherical_harmonics.num_harmonics` (published formula restated in
+    oracle/ref_shim.py); the phase function uses the reference's own constant exp(log d_n) / C_n(1) (sphere.py:159-163)."""
+
+    def __init__(self, n, order=10, projective=False):
+        self.n, self.dim, self.order, self.projective = n, n, order, projective
+        self.id = torch.zeros((1, n + 1), dtype=F64)
+        self.id[0][0] = 1.0
+        self.irreps = []
+        for index in range(order):
+            deg = 2 * index if projective else index
+            self.irreps.append((deg, self._num_harmonics(n + 1, deg), deg * (n + deg - 1)))       # sphere.py:122-127
+
+    @staticmethod
+    def _num_harmonics(dimension, degree):
+        if degree == 0:
+            return 1
+        if dimension == 3:
+            return int(2 * degree + 1)
+        return int(round((2 * degree + dimension - 2) / degree * math.comb(degree + dimension - 3, degree - 1)))
+
+    def rand(self, num=1):                                                  # sphere.py:41-46
+        x = torch.randn(num, self.n + 1, dtype=F64)
+        return x / torch.norm(x, dim=1, keepdim=True)
+
+    def pairwise_embed(self, x, y):                                         # sphere.py:48-54: all dot products, index i*M + j
+        xa, ya = pair_grid(x, y)
+        return (xa.reshape(-1, self.n + 1) * ya.reshape(-1, self.n + 1)).sum(dim=1)
+
+    def pairwise_dist(self, x, y):                                          # sphere.py:56-57 / :104-107
+        if self.projective:
+            d = torch.arccos(torch.clip(self.pairwise_embed(x, y), -1.0, 1.0))
+            return torch.min(d, REF_PI - d).reshape(x.shape[0], y.shape[0])
+        return torch.abs(torch.arccos(self.pairwise_embed(x, y))).reshape(x.shape[0], y.shape[0])
+
+    def _gegenbauer(self, deg, t):
+        """sphere.py:170-218: monomial coefficients through loggamma for degree < 25, three-term recurrence above."""
+        from scipy.special import loggamma
+        import numpy as np
+        alpha = (self.dim - 1) / 2.0
+        if deg < 25:
+            coef = torch.zeros(deg + 1, dtype=F64)
+            if deg == 0:
+                coef[0] = 1
+            if deg == 1:
+                coef[1] = 2 * alpha
+            if deg >= 2:
+                for k in range(0, deg // 2 + 1):
+                    log_c = (deg - 2 * k) * np.log(2) + loggamma(deg - k + alpha) - loggamma(alpha) - loggamma(k + 1) \
+                        - loggamma(deg - 2 * k + 1)
+                    coef[deg - 2 * k] = (-1) ** k * np.exp(log_c)
+            powers = torch.arange(0., deg + 1., dtype=F64)
+            return (torch.pow(t[..., None], powers) * coef).sum(dim=-1)
+        c = [0 * t, 2 * alpha * t]                                          # sphere.py:209-217 (starts from C_0 = 0 as written)
+        for m in range(2, deg + 1):
+            c.append((c[-1] * 2 * t * (m + alpha - 1) - (m + 2 * alpha - 2) * c[-2]) / m)
+        return c[-1]
+
+    def phase_function(self, irrep, emb):                                   # sphere.py:146-167
+        from scipy.special import loggamma
+        import numpy as np
+        deg = irrep[0]
+        if deg == 0:
+            const = 1.0
+        else:
+            log_d = np.log(2 * deg + self.dim - 1) + loggamma(deg + self.dim - 1) - loggamma(self.dim) - loggamma(deg + 1)
+            const = float(np.exp(log_d)) / float(self._gegenbauer(deg, torch.tensor(1.0, dtype=F64)))
+        return self._gegenbauer(deg, emb) * torch.tensor([const], dtype=F64)[0]
+
+
+# ----------------------------------------------------------------------------------------------------------
 # spectral_kernel.py:26-54 — EigenbasisSumKernel
 # ----------------------------------------------------------------------------------------------------------
 def eigensum_unnormalised(space, measure, x, y):

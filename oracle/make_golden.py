@@ -115,6 +115,37 @@ def main(only=None):
                         irreps=[(e.index, e.dimension, e.lb_eigenvalue) for e in space.lb_eigenspaces],
                         pairwise_dist=space.pairwise_dist(x[:16], y[:12]), dist=space.dist(x[:16], y[:16])))
 
+    # ------------------------------------------------------------------ Sphere / ProjectiveSpace zonal kernels (spaces/sphere.py)
+    from lie_stationary_kernels.spaces.sphere import Sphere, ProjectiveSpace
+    sphere_cases = [
+        ("eigsum_sphere2_heat_L15", Sphere, 2, 15, dict(kind="heat", dim=2, lengthscale=1.0, variance=5.0), 64, 50),
+        ("eigsum_sphere3_matern_L10", Sphere, 3, 10, dict(kind="matern", dim=3, lengthscale=0.5, nu=1.5, variance=4.0), 48, 40),
+        ("eigsum_sphere4_matern_L30", Sphere, 4, 30, dict(kind="matern", dim=4, lengthscale=0.6, nu=2.5), 40, 33),
+        ("eigsum_proj2_heat_L10", ProjectiveSpace, 2, 10, dict(kind="heat", dim=2, lengthscale=0.7), 48, 40),
+        ("eigsum_proj3_matern_L8", ProjectiveSpace, 3, 8, dict(kind="matern", dim=3, lengthscale=1.0, nu=2.5), 32, 32),
+    ]
+    for name, cls, n, order, mspec, nx, ny in sphere_cases:
+        if not want(name):
+            continue
+        torch.manual_seed(2468)
+        space = cls(n, order=order)
+        kern = EigenbasisSumKernel(measure_of(mspec), space)
+        kern.eval()
+        x, y = space.rand(nx), space.rand(ny)
+        y[:3] = x[:3]
+        sampler = RandomPhaseApproximation(kern, phase_order=16)
+        with torch.no_grad():
+            k_norm = kern(x, y)
+            k_raw = kern(x, y, normalize=False)
+            k_xx = kern(x[:8])
+            sample = sampler(x)
+            emb = sampler.make_embedding(x[:10])
+        save(name, dict(group=cls.__name__, n=n, order=order, measure=mspec, x=x, y=y,
+                        normalizer=kern.normalizer.detach().clone(), k_norm=k_norm, k_raw=k_raw, k_xx=k_xx,
+                        irreps=[(e.index, e.dimension, e.lb_eigenvalue) for e in space.lb_eigenspaces],
+                        phases=sampler.phases, weights=sampler.weights, sample=sample, embedding=emb,
+                        pairwise_dist=space.pairwise_dist(x[:16], y[:12]), pairwise_embed=space.pairwise_embed(x[:6], y[:5])))
+
     # ------------------------------------------------------------------ torus representatives / characters (lie_groups.py tests)
     if want("chars"):
         torch.manual_seed(7)

@@ -116,8 +116,19 @@ def _install_stubs() -> None:
             def __init__(self, *a, **k):
                 pass
 
+        def num_harmonics(dimension, degree):
+            """Published formula of the absent dependency (vdutor/SphericalHarmonics, `num_harmonics`): the number of
+            spherical harmonics of a degree in R^dimension.  It only feeds `eigenspace.dimension` of the reference's
+            Sphere (spaces/sphere.py:122-123); the kernel values do not depend on it."""
+            import math
+            if degree == 0:
+                return 1
+            if dimension == 3:
+                return int(2 * degree + 1)
+            return int(round((2 * degree + dimension - 2) / degree * math.comb(degree + dimension - 3, degree - 1)))
+
         shs.SphericalHarmonicsLevel = _Dummy
-        shs.num_harmonics = lambda *a, **k: 0
+        shs.num_harmonics = num_harmonics
         fs.FundamentalSystemCache = _Dummy
         sh.spherical_harmonics = shs
         sh.fundamental_set = fs

@@ -139,3 +139,68 @@ def test_torus_eigensum_matches_reference(name):
     assert scaled_err(orc.eigensum(space, meas, g["x"], g["y"], g["normalizer"]), g["k_norm"]) < TOL
     assert torch.equal(space.pairwise_dist(g["x"][:16], g["y"][:12]), g["pairwise_dist"])
     assert torch.equal(space.dist(g["x"][:16], g["y"][:16]), g["dist"])
+
+
+SPHERE_CASES = ["eigsum_sphere2_heat_L15", "eigsum_sphere3_matern_L10", "eigsum_sphere4_matern_L30", "eigsum_proj2_heat_L10",
+                "eigsum_proj3_matern_L8"]
+
+
+@pytest.mark.parametrize("name", SPHERE_CASES)
+def test_sphere_eigensum_matches_reference(name):
+    """oracle port of spaces/sphere.py against golden outputs of the real reference (kernel, prior sample, embedding)"""
+    g = load_golden(name)
+    space = orc.Sphere(g["n"], g["order"], projective=g["group"] == "ProjectiveSpace")
+    assert space.irreps == [tuple(i) for i in g["irreps"]]
+    meas = _measure(g["measure"])
+    assert scaled_err(orc.eigensum_unnormalised(space, meas, g["x"], g["y"]), g["k_raw"]) < TOL
+    assert scaled_err(orc.eigensum(space, meas, g["x"], g["y"], g["normalizer"]), g["k_norm"]) < TOL
+    assert torch.allclose(space.pairwise_embed(g["x"][:6], g["y"][:5]), g["pairwise_embed"], rtol=0, atol=1e-15)
+    # arccos is ill-conditioned at coinciding points (the first three): compare away from them
+    assert torch.allclose(space.pairwise_dist(g["x"][:16], g["y"][:12])[3:], g["pairwise_dist"][3:], rtol=0, atol=1e-13)
+    sample = orc.random_phase_sample(space, meas, g["phases"], g["weights"], g["x"], g["normalizer"])
+    # degrees 20-24 on S^4 go through the reference's monomial Gegenbauer form (sphere.py:170-203), whose cancellation
+    # amplifies the rounding of the summation order (vmap(dot) there, a batched sum here) to a few 1e-10
+    assert scaled_err(sample, g["sample"]) < (2e-9 if name == "eigsum_sphere4_matern_L30" else TOL)
+
+
+@pytest.mark.parametrize("n,order,projective", [(2, 15, False), (3, 24, False), (4, 40, False), (2, 12, True), (5, 10, True)])
+def test_zonal_chebyshev_plan_matches_gegenbauer(n, order, projective):
+    """host tables of spaces/sphere.py (no GPU needed): every row of the Chebyshev re-expansion, evaluated by Clenshaw in
+    float64, against a 50-digit evaluation of d_l C_l(t) / C_l(1); the oracle's restatement of the reference's monomial
+    evaluation is held to the same truth to document how far the REFERENCE is from it.  Degrees >= 25 follow the
+    reference's `NewGegenbauerPolynomials` (recurrence seeded with C_0 = 0, sphere.py:209-217), quirk G10."""
+    import mpmath
+    import numpy as np
+    from liestationarykernels_b200.spaces.sphere import _ZonalPlan, num_harmonics
+    degrees = [(2 if projective else 1) * i for i in range(order)]
+    dims = [num_harmonics(n + 1, d) for d in degrees]
+    plan = _ZonalPlan(n, degrees, dims)
+    space = orc.Sphere(n, order, projective=projective)
+    assert [i[1] for i in space.irreps] == dims
+    ts = np.concatenate([np.linspace(-1, 1, 41), [0.999999, -0.3333]])
+    mpmath.mp.dps = 50
+    alpha = mpmath.mpf(n - 1) / 2
+    worst_ours, worst_ref = 0.0, 0.0
+
+    def geg(deg, t):                       # three-term recurrence at 50 digits; degrees >= 25: the reference's C_0 = 0 seed
+        c0, c1 = mpmath.mpf(1 if deg < 25 else 0), 2 * alpha * t
+        if deg == 0:
+            return c0
+        for m in range(2, deg + 1):
+            c0, c1 = c1, (2 * t * (m + alpha - 1) * c1 - (m + 2 * alpha - 2) * c0) / m
+        return c1
+
+    for l, d in enumerate(degrees):
+        row = plan.M[l]
+        assert np.all(row[d + 1:] == 0)
+        truth = np.array([float(dims[l] * geg(d, mpmath.mpf(float(t))) / geg(d, mpmath.mpf(1))) for t in ts])
+        b1 = np.zeros_like(ts)
+        b2 = np.zeros_like(ts)
+        for k in range(d, 0, -1):
+            b1, b2 = row[k] + 2 * ts * b1 - b2, b1
+        ours = row[0] + ts * b1 - b2
+        ref = space.phase_function(space.irreps[l], torch.tensor(ts)).numpy()
+        worst_ours = max(worst_ours, np.abs(ours - truth).max() / dims[l])
+        worst_ref = max(worst_ref, np.abs(ref - truth).max() / dims[l])
+    assert worst_ours < 5e-14
+    assert worst_ref < 1e-7          # the reference's monomial form loses digits with the degree; ours does not
