@@ -66,6 +66,8 @@ typedef struct LskEpilogue {
     int32_t out_kg;                      /* PANEL_MAJOR: k-groups (4 columns) per output row */
     int32_t feat_stride;                 /* FEAT_*: column offset between irreps (= number of phases) */
     int32_t reserved;                    /* bit 0 (lsk_homog_pairs): pair (y_j, x_i) instead of (x_i, y_j);
+                                            bits 4-7 (lsk_homog_pairs, n = 5): t in {0, 2, 3}: the caller vouches that every
+                                            subgroup sample is blockdiag(I_t, R) (Stiefel: H = SO(n - m), stiefel.py:25-36);
                                             bit 1 (lsk_pairwise_poly): symmetric problem (A, B describe the same points, square
                                             row-major output): only the upper triangle of tiles is computed and mirrored;
                                             bits 8+f (lsk_pairwise_poly): form f enters the affine map squared */

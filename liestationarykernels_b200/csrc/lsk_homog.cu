@@ -397,6 +397,153 @@ homog_pair_kernel_v2(const double* __restrict__ gx, const double* __restrict__ g
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// pair kernel for SO(5)/H with the shape of the problem fixed at compile time:
+//   SHAPE: 4 bits per power b of s2 = number of powers of s1 that occur with it (the staircase of monomials of the first L
+//          irreps: L = 10 -> rows {5, 3, 2}, L = 20 -> {7, 5, 4, 3, 1}); only those monomials are averaged;
+//   MTOP:  the subgroup samples are blockdiag(I_MTOP, R_k) (Stiefel: H = SO(n - m) acts on the last n - m columns,
+//          stiefel.py:25-36), so g = M h^T differs from M only in its last n - MTOP columns: 5 (5 - MTOP)^2 multiply-adds per
+//          sample instead of 125, and tr g, tr g^2 split into a per-pair constant and a per-sample part.  MTOP = 0: general h.
+// ------------------------------------------------------------------------------------------------------------
+template <unsigned long long SHAPE> struct StairShape {
+    static constexpr int rows() { int r = 0; while (r < 16 && ((SHAPE >> (4 * r)) & 15ull)) ++r; return r; }
+    static constexpr int len(int b) { return (int)((SHAPE >> (4 * b)) & 15ull); }
+    static constexpr int offset(int b) { int o = 0; for (int q = 0; q < b; ++q) o += len(q); return o; }
+    static constexpr int total() { return offset(rows()); }
+    static constexpr int amax() { int m = 0; for (int q = 0; q < rows(); ++q) m = len(q) - 1 > m ? len(q) - 1 : m; return m; }
+};
+
+template <unsigned long long SHAPE, int MTOP>
+__global__ void __launch_bounds__(256)
+homog5_stair_kernel(const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ h,
+                    int n_rows, int n_cols, int n_avg, double* __restrict__ out, long long ld_out,
+                    const __grid_constant__ LskEpilogue p)
+{
+    constexpr int N_ = 5, W = N_ - MTOP;                         // W: columns of g that depend on the sample
+    using SH = StairShape<SHAPE>;
+    constexpr int ROWS = SH::rows(), TOTAL = SH::total(), AMAX = SH::amax();
+    constexpr int HCHUNK = 64;
+    __shared__ __align__(16) double sh[HCHUNK * N_ * W];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    const bool active = (i < n_rows) && (j < n_cols);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    double M[N_][N_];
+#pragma unroll
+    for (int a = 0; a < N_; ++a)
+#pragma unroll
+        for (int b = 0; b < N_; ++b) M[a][b] = 0.0;
+    if (active) {
+        double xi[N_][N_], yj[N_][N_];
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                xi[a][b] = gx[(size_t)i * N_ * N_ + a * N_ + b];
+                yj[a][b] = gy[(size_t)j * N_ * N_ + a * N_ + b];
+            }
+        const bool swap = (p.reserved & 1) != 0;
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < N_; ++c) s = swap ? fma(yj[c][a], xi[c][b], s) : fma(xi[c][a], yj[c][b], s);
+                M[a][b] = s;
+            }
+    }
+    // per-pair constants: the part of tr g and tr g^2 that does not see the sample
+    double t1_const = 0.0, t2_const = 0.0;
+#pragma unroll
+    for (int a = 0; a < MTOP; ++a) {
+        t1_const += M[a][a];
+#pragma unroll
+        for (int b = 0; b < MTOP; ++b) t2_const = fma(M[a][b], M[b][a], t2_const);
+    }
+    double S[TOTAL];
+#pragma unroll
+    for (int q = 0; q < TOTAL; ++q) S[q] = 0.0;
+
+    for (int k0 = 0; k0 < n_avg; k0 += HCHUNK) {
+        const int kc = min(HCHUNK, n_avg - k0);
+        __syncthreads();
+        // stage rows MTOP.. of every sample, columns MTOP.. only (the rest is the identity / zero by contract)
+        for (int q = tid; q < kc * W * W; q += 256) {
+            const int k = q / (W * W), rc = q - k * (W * W), r = rc / W, c = rc - r * W;
+            sh[q] = h[(size_t)(k0 + k) * N_ * N_ + (MTOP + r) * N_ + (MTOP + c)];
+        }
+        __syncthreads();
+        for (int k = 0; k < kc; ++k) {
+            const double* hk = sh + k * W * W;
+            // G[a][MTOP + b] = sum_c M[a][MTOP + c] h[MTOP + b][MTOP + c]
+            double G[N_][W];
+#pragma unroll
+            for (int b = 0; b < W; ++b) {
+                double hb[W];
+#pragma unroll
+                for (int c = 0; c < W; ++c) hb[c] = hk[b * W + c];
+#pragma unroll
+                for (int a = 0; a < N_; ++a) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < W; ++c) s = fma(M[a][MTOP + c], hb[c], s);
+                    G[a][b] = s;
+                }
+            }
+            double t1 = t1_const, t2 = t2_const;
+#pragma unroll
+            for (int b = 0; b < W; ++b) t1 += G[MTOP + b][b];
+#pragma unroll
+            for (int a = 0; a < MTOP; ++a)                     // cross terms: g[a][b] (changed column) * g[b][a] = M[b][a]
+#pragma unroll
+                for (int b = 0; b < W; ++b) t2 = fma(2.0 * G[a][b], M[MTOP + b][a], t2);
+#pragma unroll
+            for (int a = 0; a < W; ++a)
+#pragma unroll
+                for (int b = 0; b < W; ++b) t2 = fma(G[MTOP + a][b], G[MTOP + b][a], t2);
+            const double e2 = 0.5 * (t1 * t1 - t2);
+            const double v0 = fma(p.aff[0][2], e2, fma(p.aff[0][1], t1, p.aff[0][0]));
+            const double v1 = fma(p.aff[1][2], e2, fma(p.aff[1][1], t1, p.aff[1][0]));
+            double pa[AMAX + 1];
+            pa[0] = 1.0;
+#pragma unroll
+            for (int a = 1; a <= AMAX; ++a) pa[a] = pa[a - 1] * v0;
+            double pb = 1.0;
+#pragma unroll
+            for (int b = 0; b < ROWS; ++b) {
+#pragma unroll
+                for (int a = 0; a < SH::len(b); ++a) S[SH::offset(b) + a] = fma(pa[a], pb, S[SH::offset(b) + a]);
+                pb *= v1;
+            }
+        }
+    }
+    if (!active) return;
+    const double inv_avg = p.scale / (double)n_avg;
+    // dense copy of the averaged monomials indexed [b][a] (dynamic exponents in the coefficient loop -> local array)
+    double Sl[ROWS * (AMAX + 1)];
+#pragma unroll
+    for (int b = 0; b < ROWS; ++b)
+#pragma unroll
+        for (int a = 0; a <= AMAX; ++a) Sl[b * (AMAX + 1) + a] = a < SH::len(b) ? S[SH::offset(b) + a] * inv_avg : 0.0;
+    int pos = 0;
+    for (int l = 0; l < p.nterms; ++l) {
+        const int len = p.row_len[l];
+        double v = 0.0;
+        for (int t = 0; t < len; ++t) {
+            const unsigned long long e = (unsigned long long)__double_as_longlong(p.coef[2 * (pos + t) + 1]);
+            const int ea = (int)(e & 0xffu), eb = (int)((e >> 8) & 0xffu);
+            v = fma(p.coef[2 * (pos + t)], Sl[eb * (AMAX + 1) + ea], v);
+        }
+        pos += len;
+        const long long c = (long long)l * p.feat_stride + j;
+        double* dst = (p.out_layout == LSK_OUT_PANEL_MAJOR)
+            ? out + (((size_t)(i >> 6) * p.out_kg + (size_t)(c >> 2)) * PANEL + (i & 63)) * 4 + (c & 3)
+            : out + (size_t)i * ld_out + c;
+        *dst = v;
+    }
+}
+
 }  // namespace lsk
 
 extern "C" int lsk_lift_frames(const void* x, long long num, int n, int m, void* out, void* bad_count, void* stream) {
@@ -450,8 +597,32 @@ extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const
             amax = ea > amax ? ea : amax;
             bmax = eb > bmax ? eb : bmax;
         }
-        if (amax <= 6 && bmax <= 3)
+        // staircase of the monomials that occur: rows[b] = 1 + largest power of s1 next to s2^b
+        int rows[16] = {0};
+        bool fits16 = true;
+        for (int t = 0; t < tot; ++t) {
+            unsigned long long e;
+            memcpy(&e, &p.coef[2 * t + 1], 8);
+            const int ea = (int)(e & 0xffu), eb = (int)((e >> 8) & 0xffu);
+            if (eb >= 16 || ea >= 15) { fits16 = false; break; }
+            rows[eb] = ea + 1 > rows[eb] ? ea + 1 : rows[eb];
+        }
+        auto covered = [&](unsigned long long shape) {
+            if (!fits16) return false;
+            for (int b = 0; b < 16; ++b) if (rows[b] > (int)((shape >> (4 * b)) & 15ull)) return false;
+            return true;
+        };
+        const int mtop = (p.reserved >> 4) & 15;         // the caller vouches: samples are blockdiag(I_mtop, R)
+        constexpr unsigned long long SH10 = 0x235ull, SH20 = 0x13457ull;
+#define LSK_H5(SHAPE, MT) homog5_stair_kernel<SHAPE, MT><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p)
+        if (mtop > 4 || mtop == 1) return LSK_EARG;
+        if (covered(SH10)) {
+            if (mtop >= 3) LSK_H5(SH10, 3); else if (mtop == 2) LSK_H5(SH10, 2); else LSK_H5(SH10, 0);
+        } else if (covered(SH20)) {
+            if (mtop >= 3) LSK_H5(SH20, 3); else if (mtop == 2) LSK_H5(SH20, 2); else LSK_H5(SH20, 0);
+        } else if (amax <= 6 && bmax <= 3)
             homog_pair_kernel_v2<5, 6, 3><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
+#undef LSK_H5
         else
             homog_pair_kernel<5><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p);
     } else {

@@ -112,9 +112,29 @@ class CompactHomogeneousSpace(AbstractManifold):
     def _pairs(self, gx, gy, ep, n_rows, n_cols, out, ld):
         lib = _lib.load()
         h = self.h_samples.to(dtype).contiguous()
+        ep.reserved = (ep.reserved & ~0xf0) | (self._identity_block(h) << 4)
         _lib.check(lib.lsk_homog_pairs(_lib.ptr(gx), _lib.ptr(gy), _lib.ptr(h), n_rows, n_cols, self.n, h.shape[0],
                                        ctypes.byref(ep), ctypes.c_void_p(out), ld, _lib.stream_ptr()), "lsk_homog_pairs")
         _lib.count_launch()
+
+    def _identity_block(self, h):
+        """Largest t in {3, 2} such that every subgroup sample is blockdiag(I_t, R) — true for Stiefel manifolds, whose
+        H = SO(n - m) acts on the last n - m columns (stiefel.py:25-36) — else 0.  lsk_homog_pairs then forms only the
+        columns of lift(x)^T lift(y) h^T that depend on the sample.  Checked on the tensor itself (h_samples is a plain
+        attribute that callers may replace), once per tensor version."""
+        key = (h.data_ptr(), h._version, tuple(h.shape))
+        if getattr(self, "_hblock_key", None) != key:
+            t_found = 0
+            if self.n == 5:
+                eye = torch.eye(self.n, dtype=dtype, device=h.device)
+                for t in (3, 2):
+                    ok = torch.equal(h[:, :t, :], eye[:t, :].expand(h.shape[0], t, self.n)) and \
+                        torch.equal(h[:, t:, :t], torch.zeros_like(h[:, t:, :t]))
+                    if ok:
+                        t_found = t
+                        break
+            self._hblock_key, self._hblock = key, t_found
+        return self._hblock
 
     def _phase_features(self, x, phases, row_scales, panel):
         """Phi[n, l*P + p] = row_scales[l] * d_l * mean_k Re chi_l(lift(phase_p)^T lift(x_n) h_k^T)."""

@@ -158,3 +158,38 @@ def test_so5_dedicated_kernel_output_layouts(order):
         assert torch.equal(got, ref) and torch.isnan(odd[:, 131:]).all()
         one = kern(x[:1], y[:1])
         assert torch.equal(one, ref[:1, :1])
+
+
+def test_headline_size_sub_blocks_against_oracle():
+    """C2 at BASELINE's full size (16384 x 16384, SO(5), Matern-5/2, 100 irreps): a random 12 x 12 sub-block of the full
+    matrix against the oracle on the same points (<= 1e-10 relative per entry), the full matrix against blockwise
+    recomputation, and size-independent properties (coinciding points give the variance, translation invariance)."""
+    import lsk_oracle as orc
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    space = _space("SO", 5, 100)
+    spec = dict(kind="matern", dim=10, lengthscale=1.0, nu=2.5)
+    kern = EigenbasisSumKernel(_measure(spec), space)
+    kern.eval()
+    torch.manual_seed(21)
+    n = 16384
+    x, y = space.rand(n), space.rand(n)
+    y[100:110] = x[5000:5010]                                  # coinciding points far from the diagonal of the matrix
+    with torch.no_grad():
+        k = kern(x, y)
+        assert k.shape == (n, n)
+        assert torch.allclose(k[5000:5010, 100:110].diagonal(), torch.ones(10, dtype=torch.float64, device="cuda"), atol=1e-12)
+        ri = torch.randperm(n)[:12]
+        ci = torch.randperm(n)[:12]
+        og = orc.Group("SO", 5, 100)
+        om = orc.Measure("matern", 10, 1.0, 2.5, 1.0)
+        ref = orc.eigensum(og, om, x[ri.cuda()].cpu(), y[ci.cuda()].cpu(), orc.eigensum_normalizer(og, om))
+        got = k[ri.cuda()][:, ci.cuda()].cpu()
+        assert rel_err(got, ref) < 1e-10
+        # tiling independence: row / column blocks recomputed alone are bit-identical to the same entries of the full matrix
+        for r0, c0 in ((0, 0), (8111, 4031), (n - 517, n - 300)):
+            blk = kern(x[r0:r0 + 517].contiguous(), y[c0:c0 + 300].contiguous())
+            assert torch.equal(blk, k[r0:r0 + 517, c0:c0 + 300])
+        g = space.rand(1)
+        kc = kern(torch.matmul(g, x[9000:9256]), torch.matmul(g, y[12000:12300]))
+        assert torch.allclose(kc, k[9000:9256, 12000:12300], rtol=1e-11, atol=0)
+        assert torch.isfinite(k).all()
