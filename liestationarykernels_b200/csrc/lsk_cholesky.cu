@@ -30,6 +30,17 @@ constexpr int DIAG_SMEM = (NB * SLD + 2 * NB + 3 * NB) * 8;
 // sits at  (q / 4) * 512 + kk * 4 + q % 4.
 __device__ __forceinline__ int wg_index(int kk, int q) { return (q >> 2) * (NB * 4) + kk * 4 + (q & 3); }
 
+// 1 / d to within an ulp or two in 5 instructions (hardware seed + two Newton steps); the IEEE division sequence is ~4x
+// longer and sits on the critical path of every elimination step, in every thread
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // diagonal block
 // ------------------------------------------------------------------------------------------------------------
@@ -72,7 +83,7 @@ diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __res
                 dpiv[j] = d;
                 if (!(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);   // not positive definite (LAPACK info convention)
             }
-            const double id = 1.0 / d;
+            const double id = fast_rcp(d);
             // only entries that can lie on or above the diagonal are kept up to date: column group k reaches row group i
             // iff k >= 2 i (columns tc + 16 k, rows tr + 32 i); rows <= j are final (i < jb)
             double vc[8];

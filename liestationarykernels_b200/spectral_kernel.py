@@ -212,7 +212,7 @@ class RandomPhaseKernel(AbstractSpectralKernel):
 def _rff_scale(kernel, normalize):
     if not normalize:
         return 1.0
-    return (abs(float(kernel.measure.variance[0])) / float(kernel.normalizer)) ** 0.5
+    return (abs(float(kernel.measure.variance[0].detach())) / float(kernel.normalizer)) ** 0.5
 
 
 class RandomFourierFeatureKernel(AbstractSpectralKernel):

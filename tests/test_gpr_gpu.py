@@ -207,3 +207,53 @@ def test_gp_posterior_and_training_loop():
     assert mse < test_y.var(unbiased=False).item()          # the fitted GP beats the constant predictor
     test_ll = gpr.ExactMarginalLogLikelihood(lik, model)(pred, test_y).item()
     assert test_ll == test_ll
+
+
+@pytest.mark.parametrize("kind", ["stiefel_random_phase", "hyperbolic_rff", "sphere"])
+def test_gp_on_the_other_kernel_families(kind):
+    """examples/gpr_experiments.py:31-73 picks the kernel class by space; the GP wrapper must accept each of them (lazy Gram
+    results included); its posterior at the training inputs is checked against the closed form with a dense library solve"""
+    from liestationarykernels_b200 import gpr
+    from liestationarykernels_b200.spaces import HyperbolicSpace, Sphere, Stiefel
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel, RandomFourierFeatureKernel, RandomPhaseKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(9)
+    if kind == "stiefel_random_phase":
+        space = Stiefel(5, 3)
+        kern = RandomPhaseKernel(MaternSpectralMeasure(space.dim, 1.0, 2.5), space, phase_order=64)
+        shape = (5, 3)
+    elif kind == "hyperbolic_rff":
+        space = HyperbolicSpace(3, order=512)
+        kern = RandomFourierFeatureKernel(MaternSpectralMeasure(space.dim, 1.0, 2.5), space)
+        shape = None
+    else:
+        space = Sphere(3, order=12)
+        kern = EigenbasisSumKernel(MaternSpectralMeasure(space.dim, 1.0, 2.5), space)
+        shape = None
+    n = 40
+    x = space.rand(n).contiguous()
+    y = torch.randn(n, dtype=torch.float64, device="cuda")
+    lik = gpr.GaussianLikelihood(device="cuda")
+    flat = x.reshape(n, -1)
+    model = gpr.ExactGPModel(flat, y, lik, kern, space, point_shape=shape)
+    model.train()
+    loss = -gpr.ExactMarginalLogLikelihood(lik, model)(model(flat), y)
+    loss.backward()
+    assert torch.isfinite(loss) and lik.raw_noise.grad is not None and model.mean_module.constant.grad is not None
+    with torch.no_grad():
+        lik.raw_noise.fill_(-12.0)                      # noise -> 1e-4 + 6e-6
+    model.eval()
+    kern.eval()
+    with torch.no_grad():
+        pred = model(flat)
+    k = kern(x)
+    k = k.evaluate() if hasattr(k, "evaluate") else k
+    # the posterior at the training inputs in closed form (dense solve by the library as the independent check)
+    m = model.mean_module.constant.detach()
+    s = k + (lik.noise.detach() + 1e-6) * torch.eye(n, dtype=torch.float64, device="cuda")
+    want_mean = m + k @ torch.linalg.solve(s, y - m)
+    want_cov = k + 1e-6 * torch.eye(n, dtype=torch.float64, device="cuda") - k @ torch.linalg.solve(s, k)
+    scale = k.diagonal().mean().item()
+    assert (pred.mean - want_mean).abs().max().item() < 1e-7 * max(1.0, y.abs().max().item())
+    assert (pred.covariance_matrix - want_cov).abs().max().item() < 1e-7 * scale
+    assert pred.variance.min().item() > -1e-9 * scale
