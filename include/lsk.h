@@ -175,6 +175,13 @@ int lsk_potrf_upper(void* A, long long n, long long lda, void* work, void* info_
  * which = 1: U^T y = b;  2: U x = b;  3: both (A x = b, LAPACK dpotrs).  tmp: device scratch, n doubles. */
 int lsk_potrs_upper(const void* U, long long n, long long lda, const void* work, void* b, void* tmp, int which, void* stream);
 
+/* Dense inverse from the factor and workspace of lsk_potrf_upper (LAPACK dpotri, but the full symmetric matrix is written):
+ * out [n, ld_out] = (U^T U)^{-1}.  The gradient of the GP marginal likelihood needs it: d/dtheta log det K = tr(K^{-1} dK).
+ * work: device, lsk_potri_work_doubles(n) doubles (scratch). */
+long long lsk_potri_work_doubles(long long n);
+int lsk_potri_upper(const void* U, long long n, long long lda, const void* potrf_work, void* work, void* out, long long ld_out,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

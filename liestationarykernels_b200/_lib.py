@@ -83,6 +83,9 @@ _PROTOTYPES = {
                                        ctypes.c_void_p]),
     "lsk_potrs_upper": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "lsk_potri_work_doubles": (ctypes.c_longlong, [ctypes.c_longlong]),
+    "lsk_potri_upper": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
     "lsk_pairwise_poly": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
                                          ctypes.POINTER(LskEpilogue), ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
 }

@@ -164,16 +164,17 @@ constexpr int TRSM_THREADS = 256;
 constexpr int TRSM_SMEM = (WBLK + 32 * 64 * 4) * 8 + 16;
 
 __global__ void __launch_bounds__(TRSM_THREADS, 1)
-trsm_kernel(double* __restrict__ A, long long lda, long long n, int k0, const double* __restrict__ Wg, double* __restrict__ P,
+trsm_kernel(double* __restrict__ A, long long lda, long long n_rows, long long col0, long long col_end, int k0,
+            const double* __restrict__ Wg, double* __restrict__ P,
             int kg_stride, int g_off)         // P: panel-major with kg_stride k-groups per row; this panel fills groups g_off .. g_off + 31
-{
+{                                             // columns [col0, col_end) of the 128 rows from k0 (rows >= n_rows read as zero)
+    const long long n = col_end;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sW = reinterpret_cast<double*>(smem_raw);         // B[kk][q], k-group major (128 KB)
     double* sB = sW + WBLK;                                   // A tile, [q / 4][j][q % 4] (64 KB)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32 * 64 * 4);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const long long s = (long long)k0 + NB;                   // first trailing column
-    const long long j0 = s + 64ll * blockIdx.x;
+    const long long j0 = col0 + 64ll * blockIdx.x;
 
     if (t == 0) {
         mbar_init(bar, 1);
@@ -188,7 +189,7 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n, int k0, const do
         for (int g = t >> 6; g < 32; g += 4) {
             double v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = in ? A[(size_t)(k0 + 4 * g + e) * lda + j0 + j] : 0.0;
+            for (int e = 0; e < 4; ++e) v[e] = (in && k0 + 4 * g + e < n_rows) ? A[(size_t)(k0 + 4 * g + e) * lda + j0 + j] : 0.0;
             double2* dst = reinterpret_cast<double2*>(sB + g * 256 + j * 4);
             dst[0] = make_double2(v[0], v[1]);
             dst[1] = make_double2(v[2], v[3]);
@@ -227,6 +228,7 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n, int k0, const do
             Pp[(kk >> 2) * 256 + j * 4 + (kk & 3)] = v0;          // zero beyond column n (the A tile was zero-filled)
             Pp[(kk >> 2) * 256 + (j + 1) * 4 + (kk & 3)] = v1;
             double* dst = A + (size_t)(k0 + kk) * lda + j0 + j;
+            if (k0 + kk >= n_rows) continue;
             if (j0 + j + 1 < n && vec_ok) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
             else {
                 if (j0 + j < n) dst[0] = v0;
@@ -321,6 +323,52 @@ bwd_step_kernel(const double* __restrict__ U, long long lda, long long n, int k0
     if (sub == 0 && i < k0) r[i] -= tot;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// inverse from the factor (lsk_potri_upper): helpers
+// ------------------------------------------------------------------------------------------------------------
+// row panel of the factor, columns [col0, n), into the panel-major operand layout: P[c][kk] = U[k0 + kk][col0 + c]
+__global__ void __launch_bounds__(256)
+repack_kernel(const double* __restrict__ U, long long lda, long long n, int k0, long long col0, double* __restrict__ P)
+{
+    const int t = threadIdx.x, j = t & 63;
+    const long long c = col0 + 64ll * blockIdx.x + j;
+    double* Pp = P + (size_t)blockIdx.x * (32 * 256);
+    for (int g = t >> 6; g < 32; g += 4) {
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (c < n && k0 + 4 * g + e < n) ? U[(size_t)(k0 + 4 * g + e) * lda + c] : 0.0;
+        double2* dst = reinterpret_cast<double2*>(Pp + g * 256 + j * 4);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+identity_kernel(double* __restrict__ Y, long long n)
+{
+    const long long i = blockIdx.x, j = 256ll * blockIdx.y + threadIdx.x;
+    if (j < n) Y[i * n + j] = (i == j) ? 1.0 : 0.0;
+}
+
+// out[j][i] = out[i][j] for i < j (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+mirror_kernel(double* __restrict__ out, long long ld, long long n)
+{
+    __shared__ double tile[32][33];
+    const long long bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = 32 * bi + r, j = 32 * bj + tx;
+        tile[r][tx] = (i < n && j < n) ? out[i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long j = 32 * bj + r, i = 32 * bi + tx;        // writes out[j][i], coalesced along i
+        if (i < n && j < n && i < j) out[j * ld + i] = tile[tx][r];
+    }
+}
+
 static inline long long n_blocks(long long n) { return (n + NB - 1) / NB; }
 static inline long long panel_doubles(long long n) { return (((n + 127) / 128) * 128 + 128) * (2 * NB); }
 
@@ -368,7 +416,7 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
         diag_kernel<<<1, 512, DIAG_SMEM, st>>>(A, lda, (int)k0, nb1, W + blk * WBLK, info);
         const long long s1 = k0 + NB, m1 = n - s1;
         if (m1 <= 0) break;
-        trsm_kernel<<<(unsigned)(((m1 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, (int)k0, W + blk * WBLK, P, KG2, 0);
+        trsm_kernel<<<(unsigned)(((m1 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, s1, n, (int)k0, W + blk * WBLK, P, KG2, 0);
         // ---- strip of the next 128 rows (general accumulate, K = 128)
         const long long strip = m1 < NB ? m1 : NB;
         ep.group_end[0] = NB / 4;
@@ -380,7 +428,7 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
         const long long s2 = s1 + NB, m2 = n - s2;
         if (m2 <= 0) break;
         double* P2 = P + 2ll * KG2 * 256;                // operand rows are relative to s2: two 64-row panels further
-        trsm_kernel<<<(unsigned)(((m2 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, (int)s1, W + (blk + 1) * WBLK, P2, KG2, NB / 4);
+        trsm_kernel<<<(unsigned)(((m2 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, s2, n, (int)s1, W + (blk + 1) * WBLK, P2, KG2, NB / 4);
         // ---- trailing update (upper triangle of tiles, K = 256)
         ep.group_end[0] = KG2;
         ep.reserved = 2;
@@ -430,5 +478,61 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
         cudaError_t e = cudaMemcpyAsync(b, cur, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return (int)e;
     }
+    return (int)cudaGetLastError();
+}
+
+// Inverse from the factor: out = (U^T U)^{-1}, full symmetric n x n.  Right-looking over the 128-row blocks of the factor:
+//   Y_k,: = W_kk^T Yb_k,:                  (trsm_kernel; Yb starts as the identity and ends as U^{-T}, lower triangular)
+//   Yb_i,: -= U_k,i^T Y_k,:   for i > k    (tile kernel, read-modify-write, K = 128)
+//   out[0:n_k, 0:n_k] += Y_k,:^T Y_k,:     (tile kernel, triangular schedule: A^{-1} = U^{-1} U^{-T} = sum_k Y_k^T Y_k)
+// 2 n^3 / 3 flop, all of it on the tensor-core tile kernel; the zero structure of U^{-T} is used exactly (block level).
+extern "C" long long lsk_potri_work_doubles(long long n) {
+    using namespace lsk::chol;
+    if (n < 0) return LSK_ESIZE;
+    return ((n * n + 15) / 16) * 16 + 2 * (((n + 127) / 128) * 128) * NB;
+}
+
+extern "C" int lsk_potri_upper(const void* U_, long long n, long long lda, const void* potrf_work, void* work_, void* out_,
+                               long long ld_out, void* stream) {
+    using namespace lsk;
+    using namespace lsk::chol;
+    if (!U_ || !potrf_work || !work_ || !out_) return LSK_EARG;
+    if (n < 0 || lda < n || ld_out < n || n > 0x7fffffffLL) return LSK_ESIZE;
+    if (n == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double* U = static_cast<const double*>(U_);
+    const double* W = static_cast<const double*>(potrf_work);
+    double* Yb = static_cast<double*>(work_);
+    double* PU = Yb + ((n * n + 15) / 16) * 16;          // 128-byte aligned operands (bulk copies)
+    double* PY = PU + (((n + 127) / 128) * 128) * NB;
+    double* out = static_cast<double*>(out_);
+    cudaError_t e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset2DAsync(out, (size_t)ld_out * 8, 0, (size_t)n * 8, (size_t)n, st);
+    if (e != cudaSuccess) return (int)e;
+    identity_kernel<<<dim3((unsigned)n, (unsigned)((n + 255) / 256)), 256, 0, st>>>(Yb, n);
+
+    LskEpilogue ep = {};
+    ep.kind = LSK_EPI_SYRK; ep.nforms = 1; ep.nvars = 1; ep.nterms = 1;
+    ep.out_layout = LSK_OUT_ROW_MAJOR;
+    ep.group_begin[0] = 0; ep.group_end[0] = NB / 4;
+    const long long nblk = n_blocks(n);
+    for (long long blk = 0; blk < nblk; ++blk) {
+        const long long k0 = blk * NB;
+        const long long nk = (k0 + NB) < n ? (k0 + NB) : n;       // columns of U^{-T} that rows of this block reach
+        const long long m = n - nk;                               // rows behind the block
+        trsm_kernel<<<(unsigned)(((nk + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(Yb, n, n, 0, nk, (int)k0, W + blk * WBLK, PY, NB / 4, 0);
+        int rc;
+        if (m > 0) {
+            repack_kernel<<<(unsigned)(((m + 127) / 128) * 2), 256, 0, st>>>(U, lda, n, (int)k0, nk, PU);
+            ep.scale = -1.0; ep.reserved = 0;
+            rc = lsk_pairwise_poly(PU, PY, m, nk, NB / 4, &ep, Yb + nk * n, n, stream);
+            if (rc != 0) return rc;
+        }
+        ep.scale = 1.0; ep.reserved = 2;
+        rc = lsk_pairwise_poly(PY, PY, nk, nk, NB / 4, &ep, out, ld_out, stream);
+        if (rc != 0) return rc;
+    }
+    mirror_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32)), 256, 0, st>>>(out, ld_out, n);
     return (int)cudaGetLastError();
 }

@@ -5,9 +5,9 @@ parametrisation (`softplus(raw_noise) + 1e-4`), `covar = kernel(x) + 1e-6 I`, ex
 the number of targets, Adam + StepLR.
 
 The marginal likelihood and the posterior run on this package's fp64 Cholesky (`linalg.CholeskyFactor` ->
-`lsk_potrf_upper` / `lsk_potrs_upper`, csrc/lsk_cholesky.cu).  Hyper-parameter gradients flow through
+`lsk_potrf_upper` / `lsk_potrs_upper` / `lsk_potri_upper`, csrc/lsk_cholesky.cu).  Hyper-parameter gradients flow through
 `EigenbasisSumKernel`'s fused backward (spectral_kernel._WeightedCharacterSum); the gradient of the log-determinant needs
-the dense inverse, which is the one library call on this path (cuSOLVER potri on our factor)."""
+the dense inverse (`CholeskyFactor.inverse`)."""
 from __future__ import annotations
 
 import math

@@ -89,9 +89,16 @@ class CholeskyFactor:
         return self._solve(b, 2)
 
     def inverse(self) -> torch.Tensor:
-        """A^{-1} as a dense matrix (needed by the gradient of the marginal likelihood, tr(A^{-1} dA)).  Library call
-        (cuSOLVER potri through torch) on our factor — not one of this package's kernels."""
-        return torch.cholesky_inverse(torch.triu(self.matrix), upper=True)
+        """A^{-1} as a dense symmetric matrix (needed by the gradient of the marginal likelihood, tr(A^{-1} dA)):
+        `lsk_potri_upper`, 2 n^3 / 3 flop on the tensor-core tile kernel."""
+        lib = _lib.load()
+        out = torch.empty((self.n, self.n), dtype=F64, device=self.matrix.device)
+        if self.n:
+            work = torch.empty(lib.lsk_potri_work_doubles(self.n), dtype=F64, device=self.matrix.device)
+            _lib.check(lib.lsk_potri_upper(_lib.ptr(self.matrix), self.n, self.matrix.stride(0), _lib.ptr(self.work),
+                                           _lib.ptr(work), _lib.ptr(out), self.n, _lib.stream_ptr()), "lsk_potri_upper")
+            _lib.count_launch(4 * ((self.n + 127) // 128) + 1)
+        return out
 
 
 def cholesky(a: torch.Tensor, upper: bool = False) -> torch.Tensor:

@@ -40,6 +40,10 @@ def test_cholesky_matches_lapack(n):
     for got, want in ((f.solve(b.cuda()), x_ref), (f.solve_lower(b.cuda()), y_ref), (f.solve_upper(b.cuda()), z_ref)):
         assert (got.cpu() - want).abs().max().item() <= 1e-10 * want.abs().max().item()
     assert abs(f.logdet().item() - 2 * torch.log(torch.diagonal(ref)).sum().item()) <= 1e-10 * max(1.0, n)
+    inv_ref = torch.cholesky_inverse(ref)
+    inv = f.inverse()
+    assert torch.equal(inv, inv.mT)
+    assert (inv.cpu() - inv_ref).abs().max().item() <= 1e-10 * inv_ref.abs().max().item()
 
 
 def test_cholesky_multiple_right_hand_sides_and_strided_input():
@@ -78,6 +82,14 @@ def test_cholesky_in_place_with_leading_dimension():
     assert lib.lsk_potrf_upper(_lib.ptr(buf), n, n - 1, _lib.ptr(work), _lib.ptr(info), _lib.stream_ptr()) == -2
     assert lib.lsk_potrf_upper(None, n, lda, _lib.ptr(work), _lib.ptr(info), _lib.stream_ptr()) == -1
     assert lib.lsk_potrs_upper(_lib.ptr(buf), n, lda, _lib.ptr(work), _lib.ptr(work), _lib.ptr(work), 0, _lib.stream_ptr()) == -1
+    # inverse through the C ABI into a padded output
+    iw = torch.empty(lib.lsk_potri_work_doubles(n), dtype=torch.float64, device="cuda")
+    out = torch.full((n, lda), 3.0, dtype=torch.float64, device="cuda")
+    assert lib.lsk_potri_upper(_lib.ptr(buf), n, lda, _lib.ptr(work), _lib.ptr(iw), _lib.ptr(out), lda, _lib.stream_ptr()) == 0
+    inv_ref = torch.cholesky_inverse(ref)
+    assert (out[:, :n].cpu() - inv_ref).abs().max().item() <= 1e-10 * inv_ref.abs().max().item()
+    assert torch.all(out[:, n:] == 3.0)
+    assert lib.lsk_potri_upper(_lib.ptr(buf), n, lda, _lib.ptr(work), _lib.ptr(iw), _lib.ptr(out), n - 1, _lib.stream_ptr()) == -2
 
 
 def test_not_positive_definite_reports_lapack_info():
@@ -101,6 +113,9 @@ def test_large_factorisation_residual():
     assert ((u.mT @ u - a).abs().max() / a.abs().max()).item() < 1e-13
     b = torch.randn(n, dtype=torch.float64, device="cuda")
     assert ((a @ f.solve(b) - b).norm() / b.norm()).item() < 1e-12
+    inv = f.inverse()
+    eye = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert (a @ inv - eye).abs().max().item() < 1e-11
 
 
 def test_log_prob_and_gradients_match_lapack_autograd():

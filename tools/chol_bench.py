@@ -28,7 +28,11 @@ for n in [1, 2, 5, 64, 127, 128, 129, 255, 256, 257, 300, 1000, 1537, 2085]:
     serr = ((x - x_ref).abs().max() / x_ref.abs().max()).item()
     yerr = ((y - y_ref).abs().max() / y_ref.abs().max()).item()
     lerr = abs(f.logdet().item() - 2 * torch.log(torch.diagonal(ref)).sum().item())
-    out["parity"].append({"n": n, "L_rel": err, "solve_rel": serr, "fwd_rel": yerr, "logdet_abs": lerr, "info": f.info})
+    inv_ref = torch.cholesky_inverse(ref)
+    inv = f.inverse().cpu()
+    ierr = ((inv - inv_ref).abs().max() / inv_ref.abs().max()).item()
+    assert torch.equal(inv, inv.T)
+    out["parity"].append({"n": n, "L_rel": err, "solve_rel": serr, "fwd_rel": yerr, "logdet_abs": lerr, "inverse_rel": ierr, "info": f.info})
     print(out["parity"][-1], flush=True)
 
 # not positive definite
@@ -66,9 +70,20 @@ for n in [4096, 8192, 16384]:
     ev[0].record(); xc = torch.cholesky_solve(b[:, None], Lc); ev[1].record(); torch.cuda.synchronize()
     t_lib_solve = ev[0].elapsed_time(ev[1])
     diff = ((torch.triu(f.matrix).mT - Lc).abs().max() / Lc.abs().max()).item()
+    t_inv = 1e9
+    for it in range(2):
+        torch.cuda.synchronize()
+        ev[0].record(); inv = f.inverse(); ev[1].record(); torch.cuda.synchronize()
+        t_inv = min(t_inv, ev[0].elapsed_time(ev[1]))
+    ev[0].record(); inv_lib = torch.cholesky_inverse(Lc); ev[1].record(); torch.cuda.synchronize()
+    t_inv_lib = ev[0].elapsed_time(ev[1])
+    inv_diff = ((inv - inv_lib).abs().max() / inv_lib.abs().max()).item()
+    inv_resid = ((a @ inv[:, :64] - torch.eye(n, 64, dtype=torch.float64, device=dev)).abs().max()).item()
+    del inv, inv_lib
     rec = {"n": n, "potrf_ms": best, "tflops": n ** 3 / 3 / best / 1e9, "cusolver_potrf_ms": lib_best,
            "cusolver_tflops": n ** 3 / 3 / lib_best / 1e9, "potrs_ms": t_solve, "cusolver_potrs_ms": t_lib_solve,
-           "residual": resid, "L_vs_cusolver": diff, "info": info}
+           "residual": resid, "L_vs_cusolver": diff, "potri_ms": t_inv, "potri_tflops": 2 * n ** 3 / 3 / t_inv / 1e9,
+           "cusolver_potri_ms": t_inv_lib, "inverse_vs_cusolver": inv_diff, "inverse_residual": inv_resid, "info": info}
     out["speed"].append(rec)
     print(rec, flush=True)
     del a, work, Lc, f
