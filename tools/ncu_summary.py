@@ -23,7 +23,9 @@ def to_bytes(value, unit):
 def full(rep, out, traffic=None, kernel=None, config=None, alg_bytes=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    ti = hdr.index("gpu__time_duration.sum")
+    vals = max(rows[2:], key=lambda r: float(r[ti]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[ti], 1.0))   # longest launch of the capture
     d = {}
     for h, u, v in zip(hdr, units, vals):
         if h in KEEP or (h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h):
