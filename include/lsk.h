@@ -158,6 +158,11 @@ int lsk_haar_from_gaussian(const void* gauss, long long num, int n, int is_compl
  * spaces/su.py:47-55).  gauss: [num, 4] float64;  out: [num, 3, 3] float64 or [num, 2, 2] complex128. */
 int lsk_quaternion_to_group(const void* gauss, long long num, int to_su2, void* out, void* stream);
 
+/* Prior sample from a feature map that sits in the panel-major operand layout: out[i] = scale * sum_c A[i, c] w[c]
+ * (reference prior_approximation.py:85-88 `einsum('nm,m->n', embedding, weights)`, :114-115 for the Fourier-feature sampler).
+ * A: [n_rows] x 4 kg_total panel-major; w: device, 4 * kg_total doubles (zero beyond the last feature); HBM-bound, deterministic. */
+int lsk_panel_gemv(const void* A, long long n_rows, int kg_total, const void* w, double scale, void* out, void* stream);
+
 /* ---- GP regression step on the covariance (the caller of the hot path: reference examples/gpr_model.py:26-39 hands
  * K + sigma_n^2 I to gpytorch.models.ExactGP / ExactMarginalLogLikelihood, i.e. to a LAPACK / cuSOLVER potrf + potrs) ---- */
 

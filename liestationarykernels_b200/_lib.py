@@ -78,6 +78,8 @@ _PROTOTYPES = {
     "lsk_quaternion_to_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "lsk_torus_features": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "lsk_panel_gemv": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_double,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
     "lsk_potrf_work_doubles": (ctypes.c_longlong, [ctypes.c_longlong]),
     "lsk_potrf_upper": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]),

@@ -134,6 +134,23 @@ def gram(a: PanelMatrix, b: PanelMatrix, scale: float = 1.0, out: torch.Tensor |
     return pairwise_poly(a.buf, b.buf, a.rows, b.rows, a.kg, ep, out=out, symmetric=(a is b))
 
 
+def panel_matvec(a: PanelMatrix, w: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """scale * A w for a panel-major A [rows, cols] and a dense vector w [cols]: the prior sample `einsum('nm,m->n')` of
+    prior_approximation.py:85-88 as one HBM-bound pass over the feature map (`lsk_panel_gemv`)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    if w.numel() != a.cols:
+        raise ValueError("weight vector has %d entries, the feature map %d columns" % (w.numel(), a.cols))
+    wp = torch.zeros(a.kg * 4, dtype=F64, device=a.buf.device)
+    wp[: a.cols] = w.to(F64).reshape(-1)
+    out = torch.empty(a.rows, dtype=F64, device=a.buf.device)
+    if a.rows:
+        _lib.check(lib.lsk_panel_gemv(_lib.ptr(a.buf), a.rows, a.kg, _lib.ptr(wp), float(scale), _lib.ptr(out),
+                                      _lib.stream_ptr()), "lsk_panel_gemv")
+        _lib.count_launch()
+    return out
+
+
 def class_features(plan: GroupPlan, x: torch.Tensor, phases: torch.Tensor, row_scales, panel: bool):
     """Per-irrep class-function features  Phi[n, l * P + p] = row_scales[l] * Re chi_l(x_n phase_p^{-1})
     (`make_embedding`, spectral_kernel.py:96-109 / prior_approximation.py:70-83: irrep-major, phase-minor columns).

@@ -47,8 +47,7 @@ class RandomPhaseApproximation(torch.nn.Module):
 
     def forward(self, x):
         feats = self.kernel.manifold._phase_features(x, self.phases, self._row_scales(), panel=True)
-        w = ops.PanelMatrix.from_dense(self.weights.reshape(1, -1))
-        return ops.gram(feats, w)[:, 0]
+        return ops.panel_matvec(feats, self.weights)
 
     def _cov(self, x, y):
         scales = self._row_scales()
@@ -81,8 +80,7 @@ class RandomFourierApproximation(torch.nn.Module):
     def forward(self, x):
         m = self.kernel.manifold
         psi = m._features(m.to_group(x), m.lb_eigenspaces, self._scale(), "panel")
-        w = torch.cat((self.weights_real, -self.weights_imag)).reshape(1, -1)
-        return ops.gram(psi, ops.PanelMatrix.from_dense(w))[:, 0]
+        return ops.panel_matvec(psi, torch.cat((self.weights_real, -self.weights_imag)))
 
     def _cov(self, x, y):
         m = self.kernel.manifold
