@@ -138,6 +138,14 @@ int lsk_hyp_features(const void* x, const void* shift, const void* lmd, const vo
 int lsk_spd_features(const void* chol_upper, const void* shift_inv, const void* lmd, const void* coef, long long n_points,
                      int m, int n, double scale, void* out, int layout, long long ld_out, int out_kg, void* stream);
 
+/* Prior samples on H^n / SPD(n) with the feature map fused away: out[i] = sum_k (Re F[i,k] w[k] + Im F[i,k] w[m + k]), F as in
+ * lsk_hyp_features / lsk_spd_features (reference prior_approximation.py:107-115, RandomFourierApproximation.forward, with
+ * w = [weights_real | -weights_imag]).  The [N, m] feature matrix is never written; deterministic (no atomics). */
+int lsk_hyp_sample(const void* x, const void* shift, const void* lmd, const void* coef, const void* w, long long n_points,
+                   int m, int n, double scale, void* out, void* stream);
+int lsk_spd_sample(const void* chol_upper, const void* shift_inv, const void* lmd, const void* coef, const void* w,
+                   long long n_points, int m, int n, double scale, void* out, void* stream);
+
 /* Batched small-matrix prologues for SPD(n): mode 0 = upper Cholesky factor (reference spaces/spd.py:45-46),
  * mode 1 = inverse (spaces/spd.py:66-67).  x, out: [num, n, n]; bad_count: device int32 (not PD / singular). */
 int lsk_small_matrix(const void* x, long long num, int n, int mode, void* out, void* bad_count, void* stream);

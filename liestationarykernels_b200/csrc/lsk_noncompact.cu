@@ -33,28 +33,49 @@ __device__ __forceinline__ void store_feature(double* out, int layout, long long
     }
 }
 
-// blockDim = (64, 4): x -> feature k (fastest, coalesced), y -> point i
+// sum over the 64 threads that share threadIdx.y (two warps), fixed order: deterministic
+__device__ __forceinline__ double reduce_row_of_64(double v, double (*part)[2]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.y][threadIdx.x >> 5] = v;
+    __syncthreads();
+    return part[threadIdx.y][0] + part[threadIdx.y][1];
+}
+
+// blockDim = (64, 4): x -> feature k (fastest, coalesced), y -> point i.
+// SAMPLE: the prior sample f[i] = sum_k (Re F[i,k] w[k] + Im F[i,k] w[m + k]) is reduced in the kernel (grid.x = 1, every
+// thread strides over the features) and the feature matrix is never written (prior_approximation.py:107-115).
+template <bool SAMPLE>
 __global__ void __launch_bounds__(256)
 hyp_features_kernel(const double* __restrict__ x, const double* __restrict__ shift, const double* __restrict__ lmd,
-                    const double* __restrict__ coef, int n_points, int m, int n, double scale,
+                    const double* __restrict__ coef, const double* __restrict__ w, int n_points, int m, int n, double scale,
                     double* __restrict__ out, int layout, long long ld_out, int out_kg)
 {
-    const int k = blockIdx.x * 64 + threadIdx.x;
+    __shared__ double part[4][2];
     const int i = blockIdx.y * 4 + threadIdx.y;
-    if (i >= n_points || k >= m) return;
-    double x2 = 0.0, d2 = 0.0;
-    for (int a = 0; a < n; ++a) {
-        const double xa = x[(size_t)i * n + a];
-        const double d = xa - shift[(size_t)k * n + a];
-        x2 += xa * xa;            // sum(square(x))            (hyperbolic.py:126)
-        d2 += d * d;              // sum(square(x - b))        (hyperbolic.py:124)
-    }
-    const double log_xb = log(1.0 - x2) - log(d2);
+    const bool row_ok = i < n_points;
+    if (!SAMPLE && !row_ok) return;
     const double rho = 0.5 * (n - 1);
-    const double mag = exp(rho * log_xb) * coef[k] * scale;
-    double s, c;
-    sincos(-lmd[k] * log_xb, &s, &c);
-    store_feature(out, layout, ld_out, out_kg, i, k, m, mag * c, mag * s);
+    double acc = 0.0;
+    for (int k = blockIdx.x * 64 + threadIdx.x; k < m; k += SAMPLE ? 64 : m) {
+        double x2 = 0.0, d2 = 0.0;
+        for (int a = 0; a < n; ++a) {
+            const double xa = row_ok ? x[(size_t)i * n + a] : 0.0;
+            const double d = xa - shift[(size_t)k * n + a];
+            x2 += xa * xa;            // sum(square(x))            (hyperbolic.py:126)
+            d2 += d * d;              // sum(square(x - b))        (hyperbolic.py:124)
+        }
+        const double log_xb = log(1.0 - x2) - log(d2);
+        const double mag = exp(rho * log_xb) * coef[k] * scale;
+        double s, c;
+        sincos(-lmd[k] * log_xb, &s, &c);
+        if constexpr (SAMPLE) acc = fma(mag * c, w[k], fma(mag * s, w[m + k], acc));
+        else store_feature(out, layout, ld_out, out_kg, i, k, m, mag * c, mag * s);
+    }
+    if constexpr (SAMPLE) {
+        const double tot = reduce_row_of_64(acc, part);
+        if (threadIdx.x == 0 && row_ok) out[i] = tot;
+    }
 }
 
 // Householder QR of an N_ x N_ matrix held in registers; returns log|R_rr|
@@ -90,48 +111,59 @@ __device__ __forceinline__ void log_abs_diag_r(double (&A)[N_][N_], double (&la)
     }
 }
 
-template <int N_>
+template <int N_, bool SAMPLE>
 __global__ void __launch_bounds__(256)
 spd_features_kernel(const double* __restrict__ U, const double* __restrict__ Hinv, const double* __restrict__ lmd,
-                    const double* __restrict__ coef, int n_points, int m, double scale,
+                    const double* __restrict__ coef, const double* __restrict__ w, int n_points, int m, double scale,
                     double* __restrict__ out, int layout, long long ld_out, int out_kg)
 {
-    const int k = blockIdx.x * 64 + threadIdx.x;
+    __shared__ double part[4][2];
     const int i = blockIdx.y * 4 + threadIdx.y;
-    if (i >= n_points || k >= m) return;
-    double A[N_][N_];
-    {
-        double u[N_][N_], h[N_][N_];
+    const bool row_ok = i < n_points;
+    if (!SAMPLE && !row_ok) return;
+    double u[N_][N_];
 #pragma unroll
-        for (int a = 0; a < N_; ++a)
+    for (int a = 0; a < N_; ++a)
 #pragma unroll
-            for (int b = 0; b < N_; ++b) {
-                u[a][b] = U[(size_t)i * N_ * N_ + a * N_ + b];
-                h[a][b] = Hinv[(size_t)k * N_ * N_ + a * N_ + b];
-            }
+        for (int b = 0; b < N_; ++b) u[a][b] = row_ok ? U[(size_t)i * N_ * N_ + a * N_ + b] : (a == b ? 1.0 : 0.0);
+    double acc = 0.0;
+    for (int k = blockIdx.x * 64 + threadIdx.x; k < m; k += SAMPLE ? 64 : m) {
+        double A[N_][N_];
+        {
+            double h[N_][N_];
 #pragma unroll
-        for (int a = 0; a < N_; ++a)
+            for (int a = 0; a < N_; ++a)
 #pragma unroll
-            for (int b = 0; b < N_; ++b) {
-                double s = 0.0;
+                for (int b = 0; b < N_; ++b) h[a][b] = Hinv[(size_t)k * N_ * N_ + a * N_ + b];
 #pragma unroll
-                for (int c = 0; c < N_; ++c) s = fma(u[a][c], h[c][b], s);
-                A[a][b] = s;                                       // U_i h_k^{-1}   (space.py:338-346)
-            }
+            for (int a = 0; a < N_; ++a)
+#pragma unroll
+                for (int b = 0; b < N_; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N_; ++c) s = fma(u[a][c], h[c][b], s);
+                    A[a][b] = s;                                       // U_i h_k^{-1}   (space.py:338-346)
+                }
+        }
+        double la[N_];
+        log_abs_diag_r<N_>(A, la);
+        double re = 0.0, ph = 0.0;
+#pragma unroll
+        for (int r = 0; r < N_; ++r) {
+            const double rho = (r + 1) - 0.5 * (N_ + 1);               // spd.py:87-90
+            re = fma(rho, la[r], re);
+            ph = fma(lmd[(size_t)k * N_ + r], la[r], ph);
+        }
+        const double mag = exp(re) * coef[k] * scale;
+        double s, c;
+        sincos(ph, &s, &c);
+        if constexpr (SAMPLE) acc = fma(mag * c, w[k], fma(mag * s, w[m + k], acc));
+        else store_feature(out, layout, ld_out, out_kg, i, k, m, mag * c, mag * s);
     }
-    double la[N_];
-    log_abs_diag_r<N_>(A, la);
-    double re = 0.0, ph = 0.0;
-#pragma unroll
-    for (int r = 0; r < N_; ++r) {
-        const double rho = (r + 1) - 0.5 * (N_ + 1);               // spd.py:87-90
-        re = fma(rho, la[r], re);
-        ph = fma(lmd[(size_t)k * N_ + r], la[r], ph);
+    if constexpr (SAMPLE) {
+        const double tot = reduce_row_of_64(acc, part);
+        if (threadIdx.x == 0 && row_ok) out[i] = tot;
     }
-    const double mag = exp(re) * coef[k] * scale;
-    double s, c;
-    sincos(ph, &s, &c);
-    store_feature(out, layout, ld_out, out_kg, i, k, m, mag * c, mag * s);
 }
 
 // mode 0: upper Cholesky factor (torch.linalg.cholesky(x, upper=True), spd.py:45-46);  mode 1: inverse (spd.py:66-67)
@@ -209,9 +241,23 @@ extern "C" int lsk_hyp_features(const void* x, const void* shift, const void* lm
     if (n_points == 0 || m == 0) return 0;
     if (int rc = check_layout(layout, ld_out, m, out_kg)) return rc;
     dim3 block(64, 4), grid((unsigned)((m + 63) / 64), (unsigned)((n_points + 3) / 4));
-    hyp_features_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    hyp_features_kernel<false><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         static_cast<const double*>(x), static_cast<const double*>(shift), static_cast<const double*>(lmd),
-        static_cast<const double*>(coef), (int)n_points, m, n, scale, static_cast<double*>(out), layout, ld_out, out_kg);
+        static_cast<const double*>(coef), nullptr, (int)n_points, m, n, scale, static_cast<double*>(out), layout, ld_out, out_kg);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int lsk_hyp_sample(const void* x, const void* shift, const void* lmd, const void* coef, const void* w,
+                              long long n_points, int m, int n, double scale, void* out, void* stream) {
+    using namespace lsk;
+    if (!x || !shift || !lmd || !coef || !w || !out) return LSK_EARG;
+    if (n_points < 0 || m < 0 || n < 1 || n > 64) return LSK_ESIZE;
+    if (n_points == 0) return 0;
+    dim3 block(64, 4), grid(1, (unsigned)((n_points + 3) / 4));
+    hyp_features_kernel<true><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<const double*>(x), static_cast<const double*>(shift), static_cast<const double*>(lmd),
+        static_cast<const double*>(coef), static_cast<const double*>(w), (int)n_points, m, n, scale,
+        static_cast<double*>(out), 0, 0, 0);
     return (int)cudaGetLastError();
 }
 
@@ -230,7 +276,34 @@ extern "C" int lsk_spd_features(const void* chol_upper, const void* shift_inv, c
     const double* l = static_cast<const double*>(lmd);
     const double* c = static_cast<const double*>(coef);
     double* o = static_cast<double*>(out);
-#define LSK_SPD(N_) spd_features_kernel<N_><<<grid, block, 0, st>>>(u, h, l, c, (int)n_points, m, scale, o, layout, ld_out, out_kg)
+#define LSK_SPD(N_) spd_features_kernel<N_, false><<<grid, block, 0, st>>>(u, h, l, c, nullptr, (int)n_points, m, scale, o, layout, ld_out, out_kg)
+    switch (n) {
+    case 2: LSK_SPD(2); break;
+    case 3: LSK_SPD(3); break;
+    case 4: LSK_SPD(4); break;
+    case 5: LSK_SPD(5); break;
+    case 6: LSK_SPD(6); break;
+    default: return LSK_EUNSUPPORTED;
+    }
+#undef LSK_SPD
+    return (int)cudaGetLastError();
+}
+
+extern "C" int lsk_spd_sample(const void* chol_upper, const void* shift_inv, const void* lmd, const void* coef, const void* w,
+                              long long n_points, int m, int n, double scale, void* out, void* stream) {
+    using namespace lsk;
+    if (!chol_upper || !shift_inv || !lmd || !coef || !w || !out) return LSK_EARG;
+    if (n_points < 0 || m < 0) return LSK_ESIZE;
+    if (n_points == 0) return 0;
+    dim3 block(64, 4), grid(1, (unsigned)((n_points + 3) / 4));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double* u = static_cast<const double*>(chol_upper);
+    const double* h = static_cast<const double*>(shift_inv);
+    const double* l = static_cast<const double*>(lmd);
+    const double* c = static_cast<const double*>(coef);
+    const double* ww = static_cast<const double*>(w);
+    double* o = static_cast<double*>(out);
+#define LSK_SPD(N_) spd_features_kernel<N_, true><<<grid, block, 0, st>>>(u, h, l, c, ww, (int)n_points, m, scale, o, 0, 0, 0)
     switch (n) {
     case 2: LSK_SPD(2); break;
     case 3: LSK_SPD(3); break;

@@ -91,9 +91,8 @@ class FeatureShardedSampler:
         lo, hi = self.lo, self.hi
         if hi > lo:
             local = type(funcs)(funcs.exp.lmd[lo:hi].contiguous(), funcs.exp.shift[lo:hi].contiguous(), m, funcs.coeff[lo:hi].contiguous())
-            psi = m._features(m.to_group(x), local, s._scale(), "panel")
-            w = torch.cat((s.weights_real[lo:hi], -s.weights_imag[lo:hi])).reshape(1, -1)
-            part = ops.gram(psi, ops.PanelMatrix.from_dense(w))[:, 0].contiguous()
+            w = torch.cat((s.weights_real[lo:hi], -s.weights_imag[lo:hi]))
+            part = m._sample(m.to_group(x), local, s._scale(), w)       # feature map fused away (lsk_hyp_sample / lsk_spd_sample)
         else:
             part = torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)
         if self.world_size > 1:

@@ -107,6 +107,15 @@ class PanelMatrix:
         self.buf = torch.zeros(max(n, 1), dtype=F64, device=device) if buf is None else buf
 
     @staticmethod
+    def for_full_write(rows: int, cols: int, device) -> "PanelMatrix":
+        """Target of a kernel that writes every (row < rows, col < cols) entry: zero-filled only if the layout has padding
+        rows / columns (a feature map of C5 is 8.6 GB: the fill would cost as much as writing it)."""
+        if rows % 128 == 0 and cols % 4 == 0 and rows and cols:
+            kg, panels = cols // 4, rows // 64
+            return PanelMatrix(rows, cols, device, buf=torch.empty(panels * kg * 256, dtype=F64, device=device))
+        return PanelMatrix(rows, cols, device)
+
+    @staticmethod
     def from_dense(dense: torch.Tensor) -> "PanelMatrix":
         rows, cols = dense.shape
         pm = PanelMatrix(rows, cols, dense.device)
@@ -171,7 +180,7 @@ def features_from_operands(plan, ea: torch.Tensor, eb: torch.Tensor, N: int, P: 
         dense = features_from_operands(plan, ea, eb, N, P, row_scales, False, device)
         return PanelMatrix.from_dense(dense)
     if panel:
-        target = PanelMatrix(N, L * P, device)
+        target = PanelMatrix.for_full_write(N, L * P, device)
         out = target.buf
     else:
         target = torch.zeros((N, L * P), dtype=F64, device=device)

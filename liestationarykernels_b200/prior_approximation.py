@@ -79,8 +79,10 @@ class RandomFourierApproximation(torch.nn.Module):
 
     def forward(self, x):
         m = self.kernel.manifold
-        psi = m._features(m.to_group(x), m.lb_eigenspaces, self._scale(), "panel")
-        return ops.panel_matvec(psi, torch.cat((self.weights_real, -self.weights_imag)))
+        w = torch.cat((self.weights_real, -self.weights_imag))
+        if hasattr(m, "_sample"):          # fused: the [N, 2m] feature map is never written
+            return m._sample(m.to_group(x), m.lb_eigenspaces, self._scale(), w)
+        return ops.panel_matvec(m._features(m.to_group(x), m.lb_eigenspaces, self._scale(), "panel"), w)
 
     def _cov(self, x, y):
         m = self.kernel.manifold

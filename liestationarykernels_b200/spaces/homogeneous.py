@@ -144,7 +144,7 @@ class CompactHomogeneousSpace(AbstractManifold):
             return ops.PanelMatrix.from_dense(self._phase_features(x, phases, row_scales, False))
         gx, gp = self.M_to_G(x), self.M_to_G(phases)
         if panel:
-            target = ops.PanelMatrix(N, L * P, x.device)
+            target = ops.PanelMatrix.for_full_write(N, L * P, x.device)
             buf, ld = target.buf, 0
         else:
             target = torch.zeros((N, L * P), dtype=dtype, device=x.device)

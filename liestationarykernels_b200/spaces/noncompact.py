@@ -126,6 +126,9 @@ class HyperbolicSpace(NonCompactSymmetricSpace):
     def _features(self, x_group, funcs, scale, layout, out=None):
         return _run_features(self, "hyp", x_group.to(dtype).contiguous(), funcs, scale, layout)
 
+    def _sample(self, x_group, funcs, scale, weights):
+        return _run_sample(self, "hyp", x_group.to(dtype).contiguous(), funcs, scale, weights)
+
 
 class SymmetricPositiveDefiniteMatrices(NonCompactSymmetricSpace):
     """SPD(n) = GL(n, R)/O(n, R)  (spd.py:15-80)."""
@@ -190,6 +193,9 @@ class SymmetricPositiveDefiniteMatrices(NonCompactSymmetricSpace):
     def _features(self, x_group, funcs, scale, layout, out=None):
         return _run_features(self, "spd", x_group.to(dtype).contiguous(), funcs, scale, layout)
 
+    def _sample(self, x_group, funcs, scale, weights):
+        return _run_sample(self, "spd", x_group.to(dtype).contiguous(), funcs, scale, weights)
+
 
 def _small_matrix(x, mode, msg):
     _lib.require_cuda()
@@ -204,6 +210,33 @@ def _small_matrix(x, mode, msg):
     if int(bad.item()):
         raise RuntimeError("linalg: %s" % msg)
     return out.reshape(x.shape)
+
+
+def _run_sample(space, kind, x_group, funcs, scale, weights):
+    """f[i] = scale * sum_k (Re F[i,k] weights[k] + Im F[i,k] weights[m + k]) with the feature map fused away
+    (`lsk_hyp_sample` / `lsk_spd_sample`)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    lmd, shift, coeff = funcs.exp.lmd, funcs.exp.shift, funcs.coeff
+    m, N = lmd.shape[0], x_group.shape[0]
+    if weights.numel() != 2 * m:
+        raise ValueError("expected %d weights, got %d" % (2 * m, weights.numel()))
+    lmd_c = lmd.to(dtype).contiguous()
+    coef_c = coeff.to(dtype).reshape(-1).contiguous()
+    w = weights.to(dtype).contiguous()
+    out = torch.empty(N, dtype=dtype, device=x_group.device)
+    if N == 0:
+        return out
+    if kind == "hyp":
+        sh = shift.to(dtype).contiguous()
+        _lib.check(lib.lsk_hyp_sample(_lib.ptr(x_group), _lib.ptr(sh), _lib.ptr(lmd_c), _lib.ptr(coef_c), _lib.ptr(w), N, m,
+                                      space.n, float(scale), _lib.ptr(out), _lib.stream_ptr()), "lsk_hyp_sample")
+    else:
+        hinv = space.inv(shift)
+        _lib.check(lib.lsk_spd_sample(_lib.ptr(x_group), _lib.ptr(hinv), _lib.ptr(lmd_c), _lib.ptr(coef_c), _lib.ptr(w), N, m,
+                                      space.n, float(scale), _lib.ptr(out), _lib.stream_ptr()), "lsk_spd_sample")
+    _lib.count_launch()
+    return out
 
 
 def _run_features(space, kind, x_group, funcs, scale, layout):
@@ -223,7 +256,7 @@ def _run_features(space, kind, x_group, funcs, scale, layout):
         target = torch.empty((N, 2 * m), dtype=dtype, device=x_group.device)
         buf, code, ld, kg = target, _lib.OUT_ROW_MAJOR, 2 * m, 0
     else:
-        target = ops.PanelMatrix(N, 2 * m, x_group.device)
+        target = ops.PanelMatrix.for_full_write(N, 2 * m, x_group.device)
         buf, code, ld, kg = target.buf, _lib.OUT_PANEL_MAJOR, 0, target.kg
     if kind == "hyp":
         sh = shift.to(dtype).contiguous()
