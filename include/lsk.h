@@ -188,6 +188,12 @@ int lsk_potrf_upper(void* A, long long n, long long lda, void* work, void* info_
  * which = 1: U^T y = b;  2: U x = b;  3: both (A x = b, LAPACK dpotrs).  tmp: device scratch, n doubles. */
 int lsk_potrs_upper(const void* U, long long n, long long lda, const void* work, void* b, void* tmp, int which, void* stream);
 
+/* Forward substitution with many right-hand sides, in place: B [n, nrhs] (row-major, ldb) <- U^{-T} B = L^{-1} B — the
+ * whitening solve of the posterior covariance K** - V^T V, V = L^{-1} K*.  work: lsk_trsm_work_doubles(n, nrhs) doubles. */
+long long lsk_trsm_work_doubles(long long n, long long nrhs);
+int lsk_trsm_lower(const void* U, long long n, long long lda, const void* potrf_work, void* B, long long nrhs, long long ldb,
+                   void* work, void* stream);
+
 /* Dense inverse from the factor and workspace of lsk_potrf_upper (LAPACK dpotri, but the full symmetric matrix is written):
  * out [n, ld_out] = (U^T U)^{-1}.  The gradient of the GP marginal likelihood needs it: d/dtheta log det K = tr(K^{-1} dK).
  * work: device, lsk_potri_work_doubles(n) doubles (scratch). */

@@ -89,6 +89,9 @@ _PROTOTYPES = {
                                        ctypes.c_void_p]),
     "lsk_potrs_upper": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "lsk_trsm_work_doubles": (ctypes.c_longlong, [ctypes.c_longlong, ctypes.c_longlong]),
+    "lsk_trsm_lower": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]),
     "lsk_potri_work_doubles": (ctypes.c_longlong, [ctypes.c_longlong]),
     "lsk_potri_upper": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),

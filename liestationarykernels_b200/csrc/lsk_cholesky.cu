@@ -536,3 +536,47 @@ extern "C" int lsk_potri_upper(const void* U_, long long n, long long lda, const
     mirror_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32)), 256, 0, st>>>(out, ld_out, n);
     return (int)cudaGetLastError();
 }
+
+// Forward substitution with many right-hand sides: B [n, nrhs] (row-major, ldb) <- U^{-T} B = L^{-1} B, the whitening solve of
+// the GP posterior covariance (K** - V^T V with V = L^{-1} K*).  Same block sweep as the first phase of lsk_potri_upper:
+//   B_k,: = W_kk^T B_k,:   (trsm_kernel)      B_i,: -= U_k,i^T B_k,:  for i > k   (tile kernel, read-modify-write)
+extern "C" long long lsk_trsm_work_doubles(long long n, long long nrhs) {
+    using namespace lsk::chol;
+    if (n < 0 || nrhs < 0) return LSK_ESIZE;
+    return ((((n + 127) / 128) * 128) + (((nrhs + 127) / 128) * 128)) * NB;
+}
+
+extern "C" int lsk_trsm_lower(const void* U_, long long n, long long lda, const void* potrf_work, void* B_, long long nrhs,
+                              long long ldb, void* work_, void* stream) {
+    using namespace lsk;
+    using namespace lsk::chol;
+    if (!U_ || !potrf_work || !B_ || !work_) return LSK_EARG;
+    if (n < 0 || nrhs < 0 || lda < n || ldb < nrhs || n > 0x7fffffffLL || nrhs > 0x7fffffffLL) return LSK_ESIZE;
+    if (n == 0 || nrhs == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double* U = static_cast<const double*>(U_);
+    const double* W = static_cast<const double*>(potrf_work);
+    double* B = static_cast<double*>(B_);
+    double* PU = static_cast<double*>(work_);
+    double* PY = PU + (((n + 127) / 128) * 128) * NB;
+    cudaError_t e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    LskEpilogue ep = {};
+    ep.kind = LSK_EPI_SYRK; ep.nforms = 1; ep.nvars = 1; ep.nterms = 1;
+    ep.out_layout = LSK_OUT_ROW_MAJOR;
+    ep.group_begin[0] = 0; ep.group_end[0] = NB / 4;
+    ep.scale = -1.0; ep.reserved = 0;
+    const long long nblk = n_blocks(n);
+    for (long long blk = 0; blk < nblk; ++blk) {
+        const long long k0 = blk * NB;
+        const long long nk = (k0 + NB) < n ? (k0 + NB) : n;
+        const long long m = n - nk;
+        trsm_kernel<<<(unsigned)(((nrhs + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(B, ldb, n, 0, nrhs, (int)k0, W + blk * WBLK, PY, NB / 4, 0);
+        if (m > 0) {
+            repack_kernel<<<(unsigned)(((m + 127) / 128) * 2), 256, 0, st>>>(U, lda, n, (int)k0, nk, PU);
+            const int rc = lsk_pairwise_poly(PU, PY, m, nrhs, NB / 4, &ep, B + nk * ldb, ldb, stream);
+            if (rc != 0) return rc;
+        }
+    }
+    return (int)cudaGetLastError();
+}

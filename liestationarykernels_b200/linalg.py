@@ -81,7 +81,18 @@ class CholeskyFactor:
         return self._solve(b, 3)
 
     def solve_lower(self, b: torch.Tensor) -> torch.Tensor:
-        """L^{-1} b = U^{-T} b (the whitening solve of the posterior variance)."""
+        """L^{-1} b = U^{-T} b (the whitening solve of the posterior variance).  A matrix of right-hand sides goes through
+        the blocked `lsk_trsm_lower` (tensor-core tile kernel); a vector through the per-block matrix-vector steps."""
+        if b.dim() == 2 and b.shape[1] > 4 and self.n:
+            lib = _lib.load()
+            if b.shape[0] != self.n:
+                raise ValueError("right-hand side must have %d rows" % self.n)
+            out = b.to(F64).contiguous().clone()
+            work = torch.empty(lib.lsk_trsm_work_doubles(self.n, out.shape[1]), dtype=F64, device=out.device)
+            _lib.check(lib.lsk_trsm_lower(_lib.ptr(self.matrix), self.n, self.matrix.stride(0), _lib.ptr(self.work), _lib.ptr(out),
+                                          out.shape[1], out.stride(0), _lib.ptr(work), _lib.stream_ptr()), "lsk_trsm_lower")
+            _lib.count_launch(3 * ((self.n + 127) // 128))
+            return out
         return self._solve(b, 1)
 
     def solve_upper(self, b: torch.Tensor) -> torch.Tensor:

@@ -57,6 +57,12 @@ def test_cholesky_multiple_right_hand_sides_and_strided_input():
     b = torch.randn(300, 5, dtype=torch.float64, device="cuda")
     x = f.solve(b)
     assert ((a @ x - b).abs().max() / b.abs().max()).item() < 1e-10
+    ref = torch.linalg.cholesky(a.cpu())
+    for nrhs in (5, 64, 131, 300):                     # blocked many-right-hand-side path (lsk_trsm_lower) from 5 columns on
+        bb = torch.randn(300, nrhs, dtype=torch.float64, device="cuda")
+        want = torch.linalg.solve_triangular(ref, bb.cpu(), upper=False)
+        got = f.solve_lower(bb)
+        assert (got.cpu() - want).abs().max().item() <= 1e-10 * want.abs().max().item()
     L = cholesky(a)
     assert (L @ L.mT - a).abs().max().item() < 1e-12
     assert (cholesky(a, upper=True) - L.mT).abs().max().item() == 0.0
@@ -116,6 +122,9 @@ def test_large_factorisation_residual():
     inv = f.inverse()
     eye = torch.eye(n, dtype=torch.float64, device="cuda")
     assert (a @ inv - eye).abs().max().item() < 1e-11
+    bb = torch.randn(n, 777, dtype=torch.float64, device="cuda")
+    v = f.solve_lower(bb)
+    assert ((u.mT @ v - bb).abs().max() / bb.abs().max()).item() < 1e-12
 
 
 def test_log_prob_and_gradients_match_lapack_autograd():
