@@ -581,9 +581,10 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.group_begin[f] < 0 || p.group_end[f] > kg_total || p.group_begin[f] >= p.group_end[f]) return LSK_EARG;
     for (int f = 1; f < p.nforms; ++f)
         if (p.group_begin[f] != p.group_end[f - 1]) return LSK_EARG;   // forms tile the k range in order
-    // kg_total is the operand row stride; the forms may stop short of it (SYRK on the first half of a two-panel operand)
+    // kg_total is the operand row stride; the forms may stop short of it (SYRK on the first half of a two-panel operand,
+    // LINEAR on a column block of a feature map)
     if (p.group_begin[0] != 0 || p.group_end[p.nforms - 1] > kg_total) return LSK_EARG;
-    if (p.kind != LSK_EPI_SYRK && p.group_end[p.nforms - 1] != kg_total) return LSK_EARG;
+    if (p.kind != LSK_EPI_SYRK && p.kind != LSK_EPI_LINEAR && p.group_end[p.nforms - 1] != kg_total) return LSK_EARG;
 
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);

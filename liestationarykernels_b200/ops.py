@@ -143,6 +143,27 @@ def gram(a: PanelMatrix, b: PanelMatrix, scale: float = 1.0, out: torch.Tensor |
     return pairwise_poly(a.buf, b.buf, a.rows, b.rows, a.kg, ep, out=out, symmetric=(a is b))
 
 
+def gram_columns(a: PanelMatrix, b: PanelMatrix, g0: int, g1: int, scale: float = 1.0) -> torch.Tensor:
+    """scale * A[:, 4 g0 : 4 g1] B[:, 4 g0 : 4 g1]^T: the Gram of one column block (k-groups g0 .. g1 - 1) of two feature maps,
+    read in place — the operand pointers are advanced by g0 k-groups and the full row stride is kept."""
+    if a.kg != b.kg or not (0 <= g0 < g1 <= a.kg):
+        raise ValueError("bad column block")
+    _lib.require_cuda()
+    lib = _lib.load()
+    ep = _lib.LskEpilogue()
+    ep.kind, ep.nforms, ep.nvars, ep.nterms = _lib.EPI_LINEAR, 1, 1, 1
+    ep.group_begin[0], ep.group_end[0] = 0, g1 - g0
+    ep.scale = float(scale)
+    ep.out_layout = _lib.OUT_ROW_MAJOR
+    out = torch.empty((a.rows, b.rows), dtype=F64, device=a.buf.device)
+    if a.rows and b.rows:
+        _lib.check(lib.lsk_pairwise_poly(ctypes.c_void_p(a.buf.data_ptr() + g0 * 256 * 8), ctypes.c_void_p(b.buf.data_ptr() + g0 * 256 * 8),
+                                         a.rows, b.rows, a.kg, ctypes.byref(ep), _lib.ptr(out), out.stride(0), _lib.stream_ptr()),
+                   "lsk_pairwise_poly(column block)")
+        _lib.count_launch()
+    return out
+
+
 def panel_matvec(a: PanelMatrix, w: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     """scale * A w for a panel-major A [rows, cols] and a dense vector w [cols]: the prior sample `einsum('nm,m->n')` of
     prior_approximation.py:85-88 as one HBM-bound pass over the feature map (`lsk_panel_gemv`)."""

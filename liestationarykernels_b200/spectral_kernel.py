@@ -32,6 +32,11 @@ def spectral_weights(measure, manifold):
     return a.detach().cpu().numpy()
 
 
+def spectral_weights_tensor(measure, manifold):
+    with torch.no_grad():
+        return measure(manifold._lambdas).detach().reshape(-1)
+
+
 class _WeightedCharacterSum(torch.autograd.Function):
     """K = sum_l c_l(theta) d_l Re chi_l(x_i y_j^{-1}) with hyper-parameter gradients.
 
@@ -175,11 +180,13 @@ class RandomPhaseKernel(AbstractSpectralKernel):
         self.phase_order = phase_order
         self.phases = self.sample_phases()
         point = self.manifold.rand()
-        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+        with torch.no_grad():
+            self.normalizer = self.forward(point, point, normalize=False)[0, 0]
 
     def compute_normalizer(self):
         point = self.manifold.id
-        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+        with torch.no_grad():
+            self.normalizer = self.forward(point, point, normalize=False)[0, 0]
 
     def sample_phases(self):
         return self.manifold.rand(self.phase_order)
@@ -195,9 +202,45 @@ class RandomPhaseKernel(AbstractSpectralKernel):
         """[N, L*P] float64, irrep-major / phase-minor columns (spectral_kernel.py:96-109)."""
         return self._features(x, self._row_scales(), panel=False)
 
+    def _coefficients(self, normalize, q_identity):
+        """c_l = a_l / P  or  |sigma^2| a_l / (P norm) as a torch function of (lengthscale, variance).  In training mode the
+        normaliser is the un-normalised kernel at the identity, sum_l a_l q_l with q_l = mean_p phi_l(phase_p, id)^2,
+        recomputed from the same parameters (spectral_kernel.py:89-91, 115-117); in eval mode the stored constant."""
+        m = self.measure
+        lam = self.manifold._lambdas
+        ls, var = m.lengthscale, m.variance
+        if hasattr(m, "nu"):
+            a = torch.pow(m.nu / (ls * ls / 2.0) + lam, -m.nu - m.dim / 2)
+        else:
+            a = torch.exp(-ls * ls / 2.0 * lam)
+        if not normalize:
+            return a / self.phase_order
+        norm = (a * q_identity).sum() if q_identity is not None else torch.as_tensor(self.normalizer, dtype=dtype, device=a.device).detach()
+        return torch.abs(var[0]) * a / (self.phase_order * norm)
+
+    def _differentiable(self, x, y, normalize):
+        """forward with hyper-parameter gradients (what `examples/gpr_experiments.py` trains on homogeneous spaces)"""
+        from .lazy import DifferentiableLazyGram
+        L, P = len(self.manifold.lb_eigenspaces), self.phase_order
+        q = None
+        if self.training and normalize:
+            with torch.no_grad():
+                unit = self.manifold._phase_features(self.manifold.id, self.phases, np.ones(L), False)      # [1, L * P]
+                q = (unit.reshape(L, P) ** 2).mean(dim=1)
+        c = self._coefficients(normalize, q)
+        if q is not None:               # the state side effect of compute_normalizer (spectral_kernel.py:89-91)
+            with torch.no_grad():
+                self.normalizer = (spectral_weights_tensor(self.measure, self.manifold) * q).sum()
+        scales = np.sqrt(c.detach().cpu().numpy())
+        fx = self._features(x, scales, panel=True)
+        fy = fx if y is x else self._features(y, scales, panel=True)
+        return DifferentiableLazyGram(fx, fy, c, L, P)
+
     def forward(self, x, y=None, normalize=True):
         if y is None:
             y = x
+        if torch.is_grad_enabled() and (self.measure.lengthscale.requires_grad or self.measure.variance.requires_grad):
+            return self._differentiable(x, y, normalize)
         if self.training:
             if normalize:
                 self.compute_normalizer()

@@ -56,3 +56,50 @@ def test_random_phase_on_groups(name):
         sampler.weights = g["s_weights"].cuda()
         sample = sampler(x).cpu()
         assert scaled_err(sample, g["sample"]) < TOL
+
+
+@pytest.mark.parametrize("case,P", [("so3", 32), ("so3", 30), ("stiefel53", 16), ("sphere3", 24)])
+def test_random_phase_kernel_hyperparameter_gradients(case, P):
+    """RandomPhaseKernel in training mode (the kernel `examples/gpr_experiments.py:36-39,66-67` trains on homogeneous spaces):
+    value and lengthscale / variance gradients against torch autograd through the oracle port, normaliser recomputed at the
+    identity from the same parameters (spectral_kernel.py:89-91); P = 30 exercises the unaligned column-block path."""
+    import lsk_oracle as orc
+    from liestationarykernels_b200.spaces import SO, Sphere, Stiefel
+    from liestationarykernels_b200.spectral_kernel import RandomPhaseKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(17)
+    if case == "so3":
+        osp, space = orc.Group("SO", 3, 10), SO(3, order=10)
+    elif case == "stiefel53":
+        osp = orc.Homogeneous("stiefel", 5, 3, order=10, average_order=12)
+        space = Stiefel(5, 3, order=10, average_order=12)
+        space.h_samples = osp.h_samples.cuda()
+    else:
+        osp, space = orc.Sphere(3, 10), Sphere(3, order=10)
+    nx, ny = 37, 21
+    x, y, phases = osp.rand(nx), osp.rand(ny), osp.rand(P)
+    om = orc.Measure("matern", osp.dim, 0.7, 1.5, 1.9)
+    om.lengthscale.requires_grad_(True)
+    om.variance.requires_grad_(True)
+    norm = orc.random_phase_kernel(osp, om, phases, osp.id, osp.id)[0, 0]
+    k_ref = orc.random_phase_kernel(osp, om, phases, x, y, norm)
+    g_out = torch.randn(nx, ny, dtype=torch.float64)
+    (k_ref * g_out).sum().backward()
+    meas = MaternSpectralMeasure(osp.dim, 0.7, 1.5, 1.9)
+    kern = RandomPhaseKernel(meas, space, phase_order=P)
+    kern.phases = phases.cuda()
+    kern.train()
+    k = kern(x.cuda(), y.cuda()).evaluate()
+    assert scaled_err(k.detach().cpu(), k_ref.detach()) < TOL
+    assert abs(float(kern.normalizer) - norm.item()) < 1e-10 * abs(norm.item())
+    (k * g_out.cuda()).sum().backward()
+    for ours, ref in ((meas.lengthscale.grad, om.lengthscale.grad), (meas.variance.grad, om.variance.grad)):
+        assert ours is not None
+        assert abs(ours.item() - ref.item()) < 1e-8 * max(1.0, abs(ref.item())), (ours.item(), ref.item())
+    # eval mode: stored normaliser, still differentiable; no_grad: the plain lazy path gives the same numbers
+    kern.eval()
+    k2 = kern(x.cuda(), y.cuda()).evaluate()
+    with torch.no_grad():
+        k3 = kern(x.cuda(), y.cuda()).evaluate()
+    assert scaled_err(k2.detach().cpu(), k3.cpu()) < 1e-13
+    assert k2.requires_grad and not k3.requires_grad
