@@ -442,6 +442,31 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         // ---- class polynomial on the accumulator fragments, 8 entries at a time ----
         const int row0 = pr * BMT + wr * (8 * MT) + (lane >> 2);
         const int col0 = pc * BN + wc * 16 + 2 * (lane & 3);
+        // Gram / rank-k-update tiles that lie fully inside a row-major output: straight 16-byte stores at constant offsets
+        // from one base pointer (the general path below pays ~25 instructions of predicates and 64-bit addressing per pair,
+        // a measurable share of a K = 128 tile)
+        const bool interior_tile = vec_ok && p.out_layout == LSK_OUT_ROW_MAJOR && pr * BMT + BMT <= n_rows && pc * BN + BN <= n_cols;
+        if constexpr ((EPI == LSK_EPI_LINEAR && !SYM) || EPI == LSK_EPI_SYRK) {
+            if (interior_tile) {
+                produce_ahead();
+                double* base = out + (size_t)row0 * ld_out + col0;
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int n = 0; n < 2; ++n) {
+                        double r0, r1;
+                        if constexpr (EPI == LSK_EPI_SYRK) {
+                            r0 = fma(p.scale, acc[0][m][n][0], prev[m][n][0]);
+                            r1 = fma(p.scale, acc[0][m][n][1], prev[m][n][1]);
+                        } else {
+                            r0 = p.scale * acc[0][m][n][0];
+                            r1 = p.scale * acc[0][m][n][1];
+                        }
+                        st_cs_f64x2(base + (size_t)(m * 8) * ld_out + n * 8, r0, r1);
+                    }
+                continue;
+            }
+        }
         // writes the pair (r0, r1) at (row, col + col_shift), (row, col + col_shift + 1); `col` is even
         auto store_pair = [&](int row, int col, long long col_shift, double r0, double r1) {
             if (row >= n_rows || col >= n_cols) return;
@@ -530,13 +555,22 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                         res[e2] = o[0]; res[e2 + 1] = o[1];
                     }
                 }
+                if (!SYM && interior_tile) {          // tile fully inside a row-major output: no predicates, constant offsets
+                    double* base = out + (size_t)row0 * ld_out + col0;
 #pragma unroll
-                for (int e = 0; e < R; e += 2) {
-                    const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
-                    if constexpr (EPI == LSK_EPI_SYRK)
-                        store_pair(row0 + m * 8, col0 + n * 8, 0, fma(p.scale, res[e], prev[m][n][0]), fma(p.scale, res[e + 1], prev[m][n][1]));
-                    else
-                        store_pair(row0 + m * 8, col0 + n * 8, 0, p.scale * res[e], p.scale * res[e + 1]);
+                    for (int e = 0; e < R; e += 2) {
+                        const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
+                        st_cs_f64x2(base + (size_t)(m * 8) * ld_out + n * 8, p.scale * res[e], p.scale * res[e + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < R; e += 2) {
+                        const int m = 2 * h + (e >> 2), n = (e >> 1) & 1;
+                        if constexpr (EPI == LSK_EPI_SYRK)
+                            store_pair(row0 + m * 8, col0 + n * 8, 0, fma(p.scale, res[e], prev[m][n][0]), fma(p.scale, res[e + 1], prev[m][n][1]));
+                        else
+                            store_pair(row0 + m * 8, col0 + n * 8, 0, p.scale * res[e], p.scale * res[e + 1]);
+                    }
                 }
             }
         }
