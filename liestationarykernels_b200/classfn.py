@@ -24,6 +24,7 @@ from ._lib import (EPI_CHEB1, EPI_HORNER, EPI_ORBIT2, EPI_SPARSE, EPI_STAIR2, MA
 
 HODGE = 4       # embedding part code: Lambda^k x with the Hodge star applied to the row index (csrc/lsk_embed.cu)
 Z_SIGN = {4: -1.0, 8: 1.0}   # z = Z_SIGN * <*Lambda^r x, Lambda^r y>, matching the reference's class labelling
+SU4_REAL = 5    # embedding part code: Lambda^2 of an SU(4) element in the real basis of Lambda^2 C^4 (its SO(6) image)
 SPIN5 = 100     # embedding segment code: the 16 rotor coefficients of the Spin(5) lift (csrc/lsk_embed.cu)
 
 
@@ -81,6 +82,12 @@ class GroupPlan:
             half = n // 2
             for k in range(1, half + 1):
                 real_only = (n % 2 == 0 and k == half)
+                if n == 4 and k == 2:
+                    # Lambda^2 C^4 is a real representation (SU(4) -> SO(6)): both sides carry the real 6 x 6 image and the
+                    # form costs 36 multiply-adds instead of 72 (csrc/lsk_embed.cu, part 5)
+                    segs_a.append((2, SU4_REAL))
+                    segs_b.append((2, SU4_REAL))
+                    continue
                 segs_a.append((k, 1))
                 segs_b.append((k, 2))
                 if not real_only:
@@ -92,7 +99,7 @@ class GroupPlan:
         begin, g = [], 0
         for (k, part) in segs_a:
             begin.append(g)
-            length = 16 if k == SPIN5 else _binom(n, k) ** 2 * (2 if self.is_complex else 1)
+            length = 16 if k == SPIN5 else 36 if part == SU4_REAL else _binom(n, k) ** 2 * (2 if self.is_complex else 1)
             g += (length + 3) // 4
         self.group_begin = begin
         self.kg_total = g

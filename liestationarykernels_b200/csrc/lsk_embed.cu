@@ -226,6 +226,31 @@ embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ Embe
             const int e = (g - spec.group_begin[seg]) * 4 + j;
             if (!CPLX && spec.wedge[seg] == LSK_SEG_SPIN5) {
                 continue;                 // written by spin5_embed_kernel (one thread per point)
+            } else if (CPLX && spec.part[seg] == 5) {
+                // SU(4): Lambda^2 C^4 = C^6 carries a real structure (Hodge star composed with conjugation) that commutes
+                // with SU(4); in the basis  u_{2p} = (e_P + s_p e_P')/sqrt2,  u_{2p+1} = i (e_P - s_p e_P')/sqrt2  (P' the
+                // complementary index pair, s = +,-,+ for P = 01, 02, 03) Lambda^2 g is a REAL orthogonal 6 x 6 matrix (the
+                // double cover SU(4) -> SO(6)), and e_2(x y^{-1}) = <R(x), R(y)> costs 36 real multiply-adds instead of the
+                // 72 of the complex form.  Entry (a, b) = Re sum conj(B[I][a]) Lambda^2x[I][J] B[J][b] (2 x 2 minors).
+                if (e < 36) {
+                    const int a = e / 6, b = e - 6 * a, pa = a >> 1, pb = b >> 1;
+                    const double sa = (pa == 1) ? -1.0 : 1.0, sb = (pb == 1) ? -1.0 : 1.0;
+                    double acc = 0.0;
+                    for (int u = 0; u < 2; ++u)
+                        for (int v = 0; v < 2; ++v) {
+                            int I[4] = {0, 0, 0, 0}, J[4] = {0, 0, 0, 0};
+                            unrank(u ? 5 - pa : pa, 4, 2, I);
+                            unrank(v ? 5 - pb : pb, 4, 2, J);
+                            double re, im;
+                            minor<CPLX>(x + row * 2ll * 16, 4, 2, I, J, re, im);
+                            // conj(beta_a) beta_b with beta = (1 | s) for even columns, (i | -i s) for odd ones
+                            double car = (a & 1) ? 0.0 : (u ? sa : 1.0), cai = (a & 1) ? (u ? sa : -1.0) : 0.0;   // conj(beta_a)
+                            double cbr = (b & 1) ? 0.0 : (v ? sb : 1.0), cbi = (b & 1) ? (v ? -sb : 1.0) : 0.0;   // beta_b
+                            const double wr = car * cbr - cai * cbi, wi = car * cbi + cai * cbr;
+                            acc += wr * re - wi * im;
+                        }
+                    val = 0.5 * acc;
+                }
             } else if (e < spec.length[seg]) {
                 const int k = spec.wedge[seg], part = spec.part[seg];
                 const int C = binom(n, k);
@@ -318,11 +343,12 @@ static int make_spec(long long num, int n, int is_complex, int nseg, const int* 
             continue;
         }
         if (wedge[s] < 1 || wedge[s] > 4 || wedge[s] > n || (wedge[s] == 4 && is_complex)) return LSK_EARG;
-        if (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0 && !(part[s] == 4 && n == 2 * wedge[s]))) return LSK_EARG;
+        const bool su4_real = is_complex && part[s] == 5 && n == 4 && wedge[s] == 2;
+        if (!su4_real && (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0 && !(part[s] == 4 && n == 2 * wedge[s])))) return LSK_EARG;
         int c = 1;
         for (int i = 1; i <= wedge[s]; ++i) c = c * (n - wedge[s] + i) / i;
         spec.wedge[s] = wedge[s]; spec.part[s] = part[s]; spec.group_begin[s] = group_begin[s];
-        spec.length[s] = c * c * (is_complex ? 2 : 1);
+        spec.length[s] = su4_real ? 36 : c * c * (is_complex ? 2 : 1);
         const int end = group_begin[s] + (spec.length[s] + 3) / 4;
         if (group_begin[s] < 0 || end > kg_total) return LSK_ESIZE;
         if (s > 0 && group_begin[s] < spec.group_begin[s - 1] + (spec.length[s - 1] + 3) / 4) return LSK_EARG;

@@ -68,6 +68,16 @@ def embed(plan, x, side):
             cols.append(np.stack([spin5_rotor(xi) for xi in x]))
             continue
         c = compound(x, k)
+        if part == 5:                       # SU(4): Lambda^2 in the real basis of Lambda^2 C^4 (csrc/lsk_embed.cu, part 5)
+            s2 = 1.0 / np.sqrt(2.0)
+            B = np.zeros((6, 6), dtype=complex)
+            for p_, sg in ((0, 1.0), (1, -1.0), (2, 1.0)):
+                B[p_, 2 * p_], B[5 - p_, 2 * p_] = s2, sg * s2
+                B[p_, 2 * p_ + 1], B[5 - p_, 2 * p_ + 1] = 1j * s2, -1j * sg * s2
+            r = np.einsum("ia,nij,jb->nab", B.conj(), c, B)
+            assert np.abs(r.imag).max() < 1e-12
+            cols.append(r.real.reshape(x.shape[0], -1))
+            continue
         if part == 4:                       # Hodge star on the row index: (I, J) -> sign(I, I^c) * minor(I^c, J)
             n = x.shape[-1]
             idx = list(itertools.combinations(range(n), k))
