@@ -88,6 +88,8 @@ long long lsk_embed_buffer_doubles(long long num, int kg_total);
  * utils.py:40-52, spaces/so.py:124-127, spaces/su.py:79-82).
  * x: [num, n, n] float64 (is_complex = 0) or complex128 (is_complex = 1).  wedge/part/group_begin: host int[nseg].
  * part: 0 real; 1 complex (re,im); 2 complex (re,im) [second operand, real form]; 3 complex (-im,re) [imaginary form].
+ * parts 6..9 (complex): one real number per entry of Lambda^k x: re, im, re + im, re - im.  With A = (6, 7, 8) and B = (6, 7, 9)
+ * the complex form <Lambda^k x, conj Lambda^k y> = (f0 + f1) + i (f2 - f0 + f1) costs three real forms instead of four.
  * part 5 (complex, n = 4, wedge = 2): Lambda^2 x in the real basis of Lambda^2 C^4 (the SO(6) image of SU(4)), 36 reals, both sides.
  * part 4 (real, n = 2 * wedge): Lambda^k x with the Hodge star on the row index, so that <*Lambda^r x, Lambda^r y> is the
  * invariant prod_i 2 sin(theta_i) (up to sign) that separates the two SO(2r) classes with equal spectrum.

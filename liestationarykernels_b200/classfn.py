@@ -82,6 +82,12 @@ class GroupPlan:
             half = n // 2
             for k in range(1, half + 1):
                 real_only = (n % 2 == 0 and k == half)
+                if n == 4 and k == 1:
+                    # tr(x y^dagger) = sum (a + ib)(c - id) with three real forms instead of four (Karatsuba):
+                    #   f0 = sum a c,  f1 = sum b d,  f2 = sum (a + b)(c - d);   Re = f0 + f1,  Im = f2 - f0 + f1
+                    segs_a += [(1, 6), (1, 7), (1, 8)]
+                    segs_b += [(1, 6), (1, 7), (1, 9)]
+                    continue
                 if n == 4 and k == 2:
                     # Lambda^2 C^4 is a real representation (SU(4) -> SO(6)): both sides carry the real 6 x 6 image and the
                     # form costs 36 multiply-adds instead of 72 (csrc/lsk_embed.cu, part 5)
@@ -99,7 +105,7 @@ class GroupPlan:
         begin, g = [], 0
         for (k, part) in segs_a:
             begin.append(g)
-            length = 16 if k == SPIN5 else 36 if part == SU4_REAL else _binom(n, k) ** 2 * (2 if self.is_complex else 1)
+            length = 16 if k == SPIN5 else 36 if part == SU4_REAL else _binom(n, k) ** 2 * (2 if self.is_complex and part < 6 else 1)
             g += (length + 3) // 4
         self.group_begin = begin
         self.kg_total = g
@@ -162,6 +168,8 @@ class GroupPlan:
         self.M = np.array(mat, dtype=np.float64)
         assert np.all(np.abs(self.M) < 2.0 ** 53)
         self.aff = [[0.0] + [1.0 if f == v else 0.0 for f in range(self.nforms)] for v in range(self.nforms)]
+        if n == 4:          # forms (f0, f1, f2, e2) -> variables (Re e1, Im e1, e2), see _build_forms
+            self.aff = [[0.0, 1.0, 1.0, 0.0, 0.0], [0.0, -1.0, 1.0, 1.0, 0.0], [0.0, 0.0, 0.0, 0.0, 1.0]]
 
     def _build_so_even(self, sigs):
         """Re chi = ( P(s) + (-1)^{r/2} z Q(s) ) / 2 for even r, P(s) / 2 for odd r (invariants.so_even_character_polys);

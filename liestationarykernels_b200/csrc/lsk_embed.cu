@@ -254,7 +254,8 @@ embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ Embe
             } else if (e < spec.length[seg]) {
                 const int k = spec.wedge[seg], part = spec.part[seg];
                 const int C = binom(n, k);
-                const int el = CPLX ? (e >> 1) : e;
+                const bool one_real = CPLX && part >= 6;          // parts 6..9: one real number per complex entry
+                const int el = (CPLX && !one_real) ? (e >> 1) : e;
                 int I[4] = {0, 0, 0, 0}, J[4] = {0, 0, 0, 0};
                 unrank(el / C, n, k, I);
                 unrank(el % C, n, k, J);
@@ -277,6 +278,7 @@ embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ Embe
                 double re, im;
                 minor<CPLX>(x + row * (long long)(CPLX ? 2 : 1) * n * n, n, k, I, J, re, im);
                 if (!CPLX) val = hodge * re;
+                else if (one_real) val = part == 6 ? re : part == 7 ? im : part == 8 ? re + im : re - im;
                 else if (part == 3) val = (e & 1) ? re : -im;
                 else val = (e & 1) ? im : re;
             }
@@ -344,11 +346,12 @@ static int make_spec(long long num, int n, int is_complex, int nseg, const int* 
         }
         if (wedge[s] < 1 || wedge[s] > 4 || wedge[s] > n || (wedge[s] == 4 && is_complex)) return LSK_EARG;
         const bool su4_real = is_complex && part[s] == 5 && n == 4 && wedge[s] == 2;
-        if (!su4_real && (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0 && !(part[s] == 4 && n == 2 * wedge[s])))) return LSK_EARG;
+        const bool one_real = is_complex && part[s] >= 6 && part[s] <= 9;
+        if (!su4_real && !one_real && (is_complex ? (part[s] < 1 || part[s] > 3) : (part[s] != 0 && !(part[s] == 4 && n == 2 * wedge[s])))) return LSK_EARG;
         int c = 1;
         for (int i = 1; i <= wedge[s]; ++i) c = c * (n - wedge[s] + i) / i;
         spec.wedge[s] = wedge[s]; spec.part[s] = part[s]; spec.group_begin[s] = group_begin[s];
-        spec.length[s] = su4_real ? 36 : c * c * (is_complex ? 2 : 1);
+        spec.length[s] = su4_real ? 36 : one_real ? c * c : c * c * (is_complex ? 2 : 1);
         const int end = group_begin[s] + (spec.length[s] + 3) / 4;
         if (group_begin[s] < 0 || end > kg_total) return LSK_ESIZE;
         if (s > 0 && group_begin[s] < spec.group_begin[s - 1] + (spec.length[s - 1] + 3) / 4) return LSK_EARG;

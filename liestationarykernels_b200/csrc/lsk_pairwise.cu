@@ -678,6 +678,7 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_HORNER, 2, 2, 1);
         if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_HORNER, 3, 3, 1);
         if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_HORNER, 4, 4, 1);
+        if (p.nforms == 4 && p.nvars == 3) LSK_GO(LSK_EPI_HORNER, 4, 3, 1);        // SU(4): three-form complex trace + real e_2
         if (p.nforms == 5 && p.nvars == 5) LSK_GO(LSK_EPI_HORNER, 5, 5, 1);
         return LSK_EUNSUPPORTED;
     }
@@ -703,6 +704,7 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         if (p.nforms == 2 && p.nvars == 2) LSK_GO(LSK_EPI_FEAT_HORNER, 2, 2, 1);
         if (p.nforms == 3 && p.nvars == 3) LSK_GO(LSK_EPI_FEAT_HORNER, 3, 3, 1);
         if (p.nforms == 4 && p.nvars == 4) LSK_GO(LSK_EPI_FEAT_HORNER, 4, 4, 1);
+        if (p.nforms == 4 && p.nvars == 3) LSK_GO(LSK_EPI_FEAT_HORNER, 4, 3, 1);
         if (p.nforms == 5 && p.nvars == 5) LSK_GO(LSK_EPI_FEAT_HORNER, 5, 5, 1);
         return LSK_EUNSUPPORTED;
     }

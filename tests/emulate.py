@@ -95,6 +95,8 @@ def embed(plan, x, side):
         c = c.reshape(x.shape[0], -1)
         if part == 0 or part == 4:
             v = c.real
+        elif part >= 6:                    # one real number per complex entry: re, im, re + im, re - im
+            v = {6: c.real, 7: c.imag, 8: c.real + c.imag, 9: c.real - c.imag}[part]
         else:
             if part == 3:
                 v = np.stack((-c.imag, c.real), axis=-1).reshape(x.shape[0], -1)
