@@ -98,3 +98,86 @@ class DifferentiableLazyGram(LazyGram):
 
     def t(self):
         return DifferentiableLazyGram(self.right, self.left, self.coefficients, self.n_irreps, self.n_phases)
+
+
+class _HypGramFn(torch.autograd.Function):
+    """K = amp Re(F_x F_y^H) on hyperbolic space as a differentiable function of the spectral samples lmd [m], the
+    c-function values coeff [m] and the amplitude amp = |sigma^2| / norm:
+        F_ik = coeff_k exp((rho - i lmd_k) L_ik),   L_ik = log((1 - |x_i|^2) / |x_i - b_k|^2)     (hyperbolic.py:118-129)
+    With the upstream gradient G and T = G conj(F_y), S = G^T F_x (four real Grams on the tile kernel):
+        A_k = Re sum_i F_ik T_ik                          -> d/d amp = sum_k A_k,  d/d coeff_k = 2 amp A_k / coeff_k
+        B_k = Im sum_i L_ik F_ik T_ik,  C_k = Im sum_j L_jk conj(F_jk) S_jk     -> d/d lmd_k = amp (B_k - C_k)
+    The lengthscale reaches lmd (scaled samples) and coeff (c-function) through ordinary torch autograd on the host."""
+
+    @staticmethod
+    def forward(ctx, lmd, coeff, amp, manifold, funcs, x, y):
+        ctx.manifold, ctx.funcs, ctx.x, ctx.y = manifold, funcs, x, y
+        ctx.save_for_backward(lmd, coeff, amp)
+        s = float(amp.detach()) ** 0.5
+        px = manifold._features(manifold.to_group(x), funcs, s, "panel")
+        py = px if y is x else manifold._features(manifold.to_group(y), funcs, s, "panel")
+        return ops.gram(px, py)
+
+    @staticmethod
+    def backward(ctx, grad):
+        lmd, coeff, amp = ctx.saved_tensors
+        m, funcs, x, y = ctx.manifold, ctx.funcs, ctx.x, ctx.y
+        shift = funcs.exp.shift
+
+        def log_ratio(p):
+            pg = m.to_group(p)
+            d2 = torch.sum(torch.square(pg[:, None, :] - shift[None, :, :]), dim=-1)
+            return torch.log(1 - torch.sum(torch.square(pg), dim=1))[:, None] - torch.log(d2)
+
+        fx = m._features(m.to_group(x), funcs, 1.0, "complex")
+        fy = fx if y is x else m._features(m.to_group(y), funcs, 1.0, "complex")
+        lx = log_ratio(x)
+        ly = lx if y is x else log_ratio(y)
+        g = grad.contiguous()
+        pg, pgt = ops.PanelMatrix.from_dense(g), ops.PanelMatrix.from_dense(g.t().contiguous())
+
+        def times(pm, f):       # pm (dense operand in panel form) times the real / imaginary parts of f
+            re = ops.gram(pm, ops.PanelMatrix.from_dense(f.real.t().contiguous()))
+            im = ops.gram(pm, ops.PanelMatrix.from_dense(f.imag.t().contiguous()))
+            return re, im
+
+        t_re, t_im = times(pg, fy)                      # T = G conj(F_y) = t_re - i t_im
+        s_re, s_im = times(pgt, fx)                     # S = G^T F_x    = s_re + i s_im
+        t = torch.complex(t_re, -t_im)
+        sm = torch.complex(s_re, s_im)
+        ft = fx * t
+        a_k = ft.real.sum(dim=0)
+        b_k = (lx * ft.imag).sum(dim=0)
+        c_k = (ly * (fy.conj() * sm).imag).sum(dim=0)
+        g_amp = a_k.sum().reshape(amp.shape)
+        g_coeff = 2.0 * amp * a_k / coeff
+        g_lmd = amp * (b_k - c_k)
+        return g_lmd, g_coeff, g_amp, None, None, None, None
+
+
+class DifferentiableFourierGram(LazyGram):
+    """Lazy Gram of the hyperbolic Fourier-feature kernel whose `evaluate()` carries hyper-parameter gradients."""
+
+    def __init__(self, manifold, funcs, x, y, lmd, coeff, amp):
+        self.manifold, self.funcs, self.x, self.y = manifold, funcs, x, y
+        self.lmd, self.coeff, self.amp = lmd, coeff, amp
+        self.left = self.right = None
+        self.scale = 1.0
+
+    @property
+    def shape(self):
+        return torch.Size((self.x.shape[0], self.y.shape[0]))
+
+    def evaluate(self, out=None):
+        k = _HypGramFn.apply(self.lmd, self.coeff, self.amp, self.manifold, self.funcs, self.x, self.y)
+        if out is not None:
+            out.copy_(k.detach())
+        return k
+
+    to_dense = evaluate
+
+    def t(self):
+        return DifferentiableFourierGram(self.manifold, self.funcs, self.y, self.x, self.lmd, self.coeff, self.amp)
+
+    def __getitem__(self, idx):
+        return self.evaluate()[idx]

@@ -266,19 +266,58 @@ class RandomFourierFeatureKernel(AbstractSpectralKernel):
         super().__init__(measure, manifold)
         manifold.generate_lb_eigenspaces(measure)
         point = self.manifold.id
-        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+        with torch.no_grad():
+            self.normalizer = self.forward(point, point, normalize=False)[0, 0]
 
     def compute_normalizer(self):
         point = self.manifold.id
-        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+        with torch.no_grad():
+            self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def _differentiable(self, x, y, normalize):
+        """Hyperbolic space: forward with lengthscale / variance gradients.  The spectral samples move with the lengthscale
+        (lmd = normalised samples * scale(l), hyperbolic.py:43-52) and the c-function with them; both stay torch functions
+        of the parameters on the host, the N * M * m work of forward and backward runs on the feature and tile kernels
+        (`lazy._HypGramFn`).  Same state side effects as the plain path (features regenerated, normaliser recomputed)."""
+        from .lazy import DifferentiableFourierGram
+        from .spaces.noncompact import _SphericalFunctions
+        from .spectral_measure import MaternSpectralMeasure
+        m, meas = self.manifold, self.measure
+        if m.normalized_lmd is None:
+            m._generate_lb_eigenspace(meas)
+        if isinstance(meas, MaternSpectralMeasure):
+            scale = torch.sqrt(1 / 4 + 2 * meas.nu[0] / (meas.lengthscale[0] ** 2))
+        else:
+            scale = 1.0 / torch.abs(meas.lengthscale[0])
+        if self.training:
+            lmd = m.normalized_lmd.detach() * scale
+        else:           # eval mode keeps the features of the last generate_lb_eigenspaces call; gradients still flow via scale
+            lmd = m.lb_eigenspaces.exp.lmd.detach() / scale.detach() * scale
+        coeff = m.c_function(lmd)
+        funcs = _SphericalFunctions(lmd.detach(), m.shift if self.training else m.lb_eigenspaces.exp.shift, m, coeff.detach())
+        if self.training:
+            m.lb_eigenspaces = funcs
+        if normalize:
+            if self.training:
+                norm = (coeff * coeff).sum()
+                self.normalizer = norm.detach()
+            else:
+                norm = torch.as_tensor(self.normalizer, dtype=dtype, device=lmd.device).detach()
+            amp = torch.abs(meas.variance[0]) / norm
+        else:
+            amp = torch.ones((), dtype=dtype, device=lmd.device)
+        return DifferentiableFourierGram(m, funcs, x, y, lmd, coeff, amp)
 
     def forward(self, x, y=None, normalize=True):
+        if y is None:
+            y = x
+        if torch.is_grad_enabled() and hasattr(self.manifold, "normalized_lmd") and \
+                (self.measure.lengthscale.requires_grad or self.measure.variance.requires_grad):
+            return self._differentiable(x, y, normalize)
         if self.training:
             self.manifold.generate_lb_eigenspaces(self.measure)
             if normalize:
                 self.compute_normalizer()
-        if y is None:
-            y = x
         manifold = self.manifold
         s = _rff_scale(self, normalize)
         px = manifold._features(manifold.to_group(x), manifold.lb_eigenspaces, s, "panel")

@@ -264,8 +264,8 @@ def test_gp_on_the_other_kernel_families(kind):
     loss = -gpr.ExactMarginalLogLikelihood(lik, model)(model(flat), y)
     loss.backward()
     assert torch.isfinite(loss) and lik.raw_noise.grad is not None and model.mean_module.constant.grad is not None
-    if kind != "hyperbolic_rff":        # lengthscale gradients flow through EigenbasisSumKernel and RandomPhaseKernel
-        assert kern.measure.lengthscale.grad is not None and torch.isfinite(kern.measure.lengthscale.grad).all()
+    # lengthscale gradients flow through EigenbasisSumKernel, RandomPhaseKernel and the hyperbolic Fourier-feature kernel
+    assert kern.measure.lengthscale.grad is not None and torch.isfinite(kern.measure.lengthscale.grad).all()
     with torch.no_grad():
         lik.raw_noise.fill_(-12.0)                      # noise -> 1e-4 + 6e-6
     model.eval()

@@ -85,3 +85,44 @@ def test_hyperbolic_rff_and_pairwise_kernels_agree():
         a, b = k1(x, x).evaluate(), k2(x, x)
     assert torch.allclose(torch.diagonal(b), torch.ones(10, dtype=torch.float64, device="cuda"), atol=1e-9)
     assert (a - b).abs().max().item() < 0.1, (a - b).abs().max().item()
+
+
+@pytest.mark.parametrize("kind,n,m", [("matern", 3, 64), ("heat", 2, 48), ("matern", 4, 40)])
+def test_hyperbolic_fourier_kernel_hyperparameter_gradients(kind, n, m):
+    """RandomFourierFeatureKernel on H^n in training mode (what `examples/hyperbolic_GPR.ipynb` / gpr_experiments.py train):
+    value, lengthscale and variance gradients against torch autograd through the oracle port — the spectral samples scale
+    with the lengthscale (hyperbolic.py:43-52), the c-function and the normaliser move with them."""
+    import lsk_oracle as orc
+    from liestationarykernels_b200.spaces import HyperbolicSpace
+    from liestationarykernels_b200.spectral_kernel import RandomFourierFeatureKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure, SqExpSpectralMeasure
+    torch.manual_seed(23)
+    oh = orc.Hyperbolic(n, order=m)
+    om = orc.Measure(kind, n, 0.8, 1.5 if kind == "matern" else None, 1.6)
+    om.lengthscale.requires_grad_(True)
+    om.variance.requires_grad_(True)
+    nx, ny = 33, 19
+    x, y = oh.rand(nx), oh.rand(ny)
+    lmd, shift = oh.generate(om)
+    norm = orc.rff_normalizer(oh, lmd, shift)
+    k_ref = orc.rff_kernel(oh, om, lmd, shift, x, y, norm)
+    g_out = torch.randn(nx, ny, dtype=torch.float64)
+    (k_ref * g_out).sum().backward()
+    space = HyperbolicSpace(n, order=m)
+    space.normalized_lmd, space.shift = oh.normalized_lmd.cuda(), oh.shift.cuda()      # same-tensor rule
+    meas = MaternSpectralMeasure(n, 0.8, 1.5, 1.6) if kind == "matern" else SqExpSpectralMeasure(n, 0.8, 1.6)
+    kern = RandomFourierFeatureKernel(meas, space)
+    kern.train()
+    k = kern(x.cuda(), y.cuda()).evaluate()
+    assert scaled_err(k.detach().cpu(), k_ref.detach()) < 1e-10
+    assert abs(float(kern.normalizer) - norm.item()) < 1e-10 * abs(norm.item())
+    (k * g_out.cuda()).sum().backward()
+    for ours, ref in ((meas.lengthscale.grad, om.lengthscale.grad), (meas.variance.grad, om.variance.grad)):
+        assert ours is not None
+        assert abs(ours.item() - ref.item()) < 1e-8 * max(1.0, abs(ref.item())), (ours.item(), ref.item())
+    # symmetric call and eval mode
+    kern.eval()
+    kxx = kern(x.cuda()).evaluate()
+    with torch.no_grad():
+        plain = kern(x.cuda()).evaluate()
+    assert kxx.requires_grad and scaled_err(kxx.detach().cpu(), plain.cpu()) < 1e-13
