@@ -149,6 +149,10 @@ int lsk_hyp_sample(const void* x, const void* shift, const void* lmd, const void
 int lsk_spd_sample(const void* chol_upper, const void* shift_inv, const void* lmd, const void* coef, const void* w,
                    long long n_points, int m, int n, double scale, void* out, void* stream);
 
+/* Iwasawa logarithms log a_r(U_i Hinv_k), out [n_points, m, n]: what the hyper-parameter gradient of the SPD Fourier-feature
+ * kernel needs next to the features (dF/dlambda_kr = i log a_r F; reference spd.py:92-106 under torch autograd). */
+int lsk_spd_logdiag(const void* chol_upper, const void* shift_inv, long long n_points, int m, int n, void* out, void* stream);
+
 /* Batched small-matrix prologues for SPD(n): mode 0 = upper Cholesky factor (reference spaces/spd.py:45-46),
  * mode 1 = inverse (spaces/spd.py:66-67).  x, out: [num, n, n]; bad_count: device int32 (not PD / singular). */
 int lsk_small_matrix(const void* x, long long num, int n, int mode, void* out, void* bad_count, void* stream);

@@ -166,6 +166,41 @@ spd_features_kernel(const double* __restrict__ U, const double* __restrict__ Hin
     }
 }
 
+// log a_r(U_i h_k^{-1}) for every (point, feature): the Iwasawa logarithms the gradient of the SPD Fourier-feature kernel
+// needs (dF/dlambda_kr = i log a_r F);  out[i, k, r]
+template <int N_>
+__global__ void __launch_bounds__(256)
+spd_logdiag_kernel(const double* __restrict__ U, const double* __restrict__ Hinv, int n_points, int m, double* __restrict__ out)
+{
+    const int k = blockIdx.x * 64 + threadIdx.x;
+    const int i = blockIdx.y * 4 + threadIdx.y;
+    if (i >= n_points || k >= m) return;
+    double A[N_][N_];
+    {
+        double u[N_][N_], h[N_][N_];
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                u[a][b] = U[(size_t)i * N_ * N_ + a * N_ + b];
+                h[a][b] = Hinv[(size_t)k * N_ * N_ + a * N_ + b];
+            }
+#pragma unroll
+        for (int a = 0; a < N_; ++a)
+#pragma unroll
+            for (int b = 0; b < N_; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < N_; ++c) s = fma(u[a][c], h[c][b], s);
+                A[a][b] = s;
+            }
+    }
+    double la[N_];
+    log_abs_diag_r<N_>(A, la);
+#pragma unroll
+    for (int r = 0; r < N_; ++r) out[((size_t)i * m + k) * N_ + r] = la[r];
+}
+
 // mode 0: upper Cholesky factor (torch.linalg.cholesky(x, upper=True), spd.py:45-46);  mode 1: inverse (spd.py:66-67)
 __global__ void __launch_bounds__(128)
 small_matrix_kernel(const double* __restrict__ x, long long num, int n, int mode, double* __restrict__ out, int* __restrict__ bad) {
@@ -304,6 +339,30 @@ extern "C" int lsk_spd_sample(const void* chol_upper, const void* shift_inv, con
     const double* ww = static_cast<const double*>(w);
     double* o = static_cast<double*>(out);
 #define LSK_SPD(N_) spd_features_kernel<N_, true><<<grid, block, 0, st>>>(u, h, l, c, ww, (int)n_points, m, scale, o, 0, 0, 0)
+    switch (n) {
+    case 2: LSK_SPD(2); break;
+    case 3: LSK_SPD(3); break;
+    case 4: LSK_SPD(4); break;
+    case 5: LSK_SPD(5); break;
+    case 6: LSK_SPD(6); break;
+    default: return LSK_EUNSUPPORTED;
+    }
+#undef LSK_SPD
+    return (int)cudaGetLastError();
+}
+
+extern "C" int lsk_spd_logdiag(const void* chol_upper, const void* shift_inv, long long n_points, int m, int n, void* out,
+                               void* stream) {
+    using namespace lsk;
+    if (!chol_upper || !shift_inv || !out) return LSK_EARG;
+    if (n_points < 0 || m < 0) return LSK_ESIZE;
+    if (n_points == 0 || m == 0) return 0;
+    dim3 block(64, 4), grid((unsigned)((m + 63) / 64), (unsigned)((n_points + 3) / 4));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double* u = static_cast<const double*>(chol_upper);
+    const double* h = static_cast<const double*>(shift_inv);
+    double* o = static_cast<double*>(out);
+#define LSK_SPD(N_) spd_logdiag_kernel<N_><<<grid, block, 0, st>>>(u, h, (int)n_points, m, o)
     switch (n) {
     case 2: LSK_SPD(2); break;
     case 3: LSK_SPD(3); break;

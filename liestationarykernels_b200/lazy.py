@@ -100,13 +100,14 @@ class DifferentiableLazyGram(LazyGram):
         return DifferentiableLazyGram(self.right, self.left, self.coefficients, self.n_irreps, self.n_phases)
 
 
-class _HypGramFn(torch.autograd.Function):
-    """K = amp Re(F_x F_y^H) on hyperbolic space as a differentiable function of the spectral samples lmd [m], the
-    c-function values coeff [m] and the amplitude amp = |sigma^2| / norm:
-        F_ik = coeff_k exp((rho - i lmd_k) L_ik),   L_ik = log((1 - |x_i|^2) / |x_i - b_k|^2)     (hyperbolic.py:118-129)
+class _FourierGramFn(torch.autograd.Function):
+    """K = amp Re(F_x F_y^H) on a non-compact symmetric space as a differentiable function of the spectral samples lmd
+    ([m] on H^n, [m, n] on SPD(n)), the c-function values coeff [m] and the amplitude amp = |sigma^2| / norm.
+        dF_ik / dlmd_kr = i D_ikr F_ik,   D = -log((1 - |x|^2) / |x - b|^2) on H^n (hyperbolic.py:118-129),
+                                          D_r = log a_r(U_i h_k^{-1}) on SPD(n) (spd.py:92-106)
     With the upstream gradient G and T = G conj(F_y), S = G^T F_x (four real Grams on the tile kernel):
-        A_k = Re sum_i F_ik T_ik                          -> d/d amp = sum_k A_k,  d/d coeff_k = 2 amp A_k / coeff_k
-        B_k = Im sum_i L_ik F_ik T_ik,  C_k = Im sum_j L_jk conj(F_jk) S_jk     -> d/d lmd_k = amp (B_k - C_k)
+        A_k  = Re sum_i F_ik T_ik                              -> d/d amp = sum_k A_k,  d/d coeff_k = 2 amp A_k / coeff_k
+        B_kr = Im sum_i D_ikr F_ik T_ik,  C_kr = Im sum_j D_jkr conj(F_jk) S_jk      -> d/d lmd_kr = -amp (B_kr - C_kr)
     The lengthscale reaches lmd (scaled samples) and coeff (c-function) through ordinary torch autograd on the host."""
 
     @staticmethod
@@ -122,41 +123,33 @@ class _HypGramFn(torch.autograd.Function):
     def backward(ctx, grad):
         lmd, coeff, amp = ctx.saved_tensors
         m, funcs, x, y = ctx.manifold, ctx.funcs, ctx.x, ctx.y
-        shift = funcs.exp.shift
-
-        def log_ratio(p):
-            pg = m.to_group(p)
-            d2 = torch.sum(torch.square(pg[:, None, :] - shift[None, :, :]), dim=-1)
-            return torch.log(1 - torch.sum(torch.square(pg), dim=1))[:, None] - torch.log(d2)
-
         fx = m._features(m.to_group(x), funcs, 1.0, "complex")
         fy = fx if y is x else m._features(m.to_group(y), funcs, 1.0, "complex")
-        lx = log_ratio(x)
-        ly = lx if y is x else log_ratio(y)
+        dx = m._log_terms(x, funcs)                         # [N, m, R]
+        dy = dx if y is x else m._log_terms(y, funcs)
         g = grad.contiguous()
         pg, pgt = ops.PanelMatrix.from_dense(g), ops.PanelMatrix.from_dense(g.t().contiguous())
 
-        def times(pm, f):       # pm (dense operand in panel form) times the real / imaginary parts of f
+        def times(pm, f):       # (dense operand in panel form) times the real / imaginary parts of f
             re = ops.gram(pm, ops.PanelMatrix.from_dense(f.real.t().contiguous()))
             im = ops.gram(pm, ops.PanelMatrix.from_dense(f.imag.t().contiguous()))
             return re, im
 
         t_re, t_im = times(pg, fy)                      # T = G conj(F_y) = t_re - i t_im
         s_re, s_im = times(pgt, fx)                     # S = G^T F_x    = s_re + i s_im
-        t = torch.complex(t_re, -t_im)
-        sm = torch.complex(s_re, s_im)
-        ft = fx * t
+        ft = fx * torch.complex(t_re, -t_im)
+        fs = fy.conj() * torch.complex(s_re, s_im)
         a_k = ft.real.sum(dim=0)
-        b_k = (lx * ft.imag).sum(dim=0)
-        c_k = (ly * (fy.conj() * sm).imag).sum(dim=0)
+        b_kr = (dx * ft.imag[:, :, None]).sum(dim=0)
+        c_kr = (dy * fs.imag[:, :, None]).sum(dim=0)
         g_amp = a_k.sum().reshape(amp.shape)
         g_coeff = 2.0 * amp * a_k / coeff
-        g_lmd = amp * (b_k - c_k)
+        g_lmd = (-amp * (b_kr - c_kr)).reshape(lmd.shape)
         return g_lmd, g_coeff, g_amp, None, None, None, None
 
 
 class DifferentiableFourierGram(LazyGram):
-    """Lazy Gram of the hyperbolic Fourier-feature kernel whose `evaluate()` carries hyper-parameter gradients."""
+    """Lazy Gram of the Fourier-feature kernel on H^n / SPD(n) whose `evaluate()` carries hyper-parameter gradients."""
 
     def __init__(self, manifold, funcs, x, y, lmd, coeff, amp):
         self.manifold, self.funcs, self.x, self.y = manifold, funcs, x, y
@@ -169,7 +162,7 @@ class DifferentiableFourierGram(LazyGram):
         return torch.Size((self.x.shape[0], self.y.shape[0]))
 
     def evaluate(self, out=None):
-        k = _HypGramFn.apply(self.lmd, self.coeff, self.amp, self.manifold, self.funcs, self.x, self.y)
+        k = _FourierGramFn.apply(self.lmd, self.coeff, self.amp, self.manifold, self.funcs, self.x, self.y)
         if out is not None:
             out.copy_(k.detach())
         return k

@@ -79,6 +79,27 @@ class HyperbolicSpace(NonCompactSymmetricSpace):
         lmd = (self.normalized_lmd * scale).detach()
         self.lb_eigenspaces = _SphericalFunctions(lmd, self.shift, self, self.c_function(lmd))
 
+    def _differentiable_spectrum(self, measure, resample):
+        """(lmd, shift, coeff) with lmd and coeff attached to the autograd graph of the lengthscale (the normalised samples
+        are drawn once and cached, hyperbolic.py:27-52; eval mode keeps the features of the last generation)."""
+        if self.normalized_lmd is None:
+            self._generate_lb_eigenspace(measure)
+        if isinstance(measure, MaternSpectralMeasure):
+            scale = torch.sqrt(1 / 4 + 2 * measure.nu[0] / (measure.lengthscale[0] ** 2))
+        else:
+            scale = 1.0 / torch.abs(measure.lengthscale[0])
+        if resample:
+            lmd, shift = self.normalized_lmd.detach() * scale, self.shift
+        else:
+            lmd, shift = self.lb_eigenspaces.exp.lmd.detach() * (scale / scale.detach()), self.lb_eigenspaces.exp.shift
+        return lmd, shift, self.c_function(lmd)
+
+    def _log_terms(self, x, funcs):
+        """L[i, k] = log((1 - |x_i|^2) / |x_i - b_k|^2): dF_ik / dlmd_k = -i L_ik F_ik"""
+        pg, shift = self.to_group(x), funcs.exp.shift
+        d2 = torch.sum(torch.square(pg[:, None, :] - shift[None, :, :]), dim=-1)
+        return -(torch.log(1 - torch.sum(torch.square(pg), dim=1))[:, None] - torch.log(d2))[:, :, None]
+
     def c_function(self, lmd):
         """|c(lambda)|^{-1} up to constants (hyperbolic.py:134-150)."""
         n = self.n
@@ -140,21 +161,60 @@ class SymmetricPositiveDefiniteMatrices(NonCompactSymmetricSpace):
         self.order = order
         self.id = torch.eye(self.n, device=cuda_device(), dtype=dtype).view(1, self.n, self.n)
 
-    def generate_lb_eigenspaces(self, measure):
+    def _draw(self, measure):
+        """The random part of spd.py:27-43 in the reference's RNG order: shifts, GOE spectra, chi^2 mixing (Matern only)."""
         from ..utils import GOE_sampler
         shift = self.rand_phase(self.order)
+        goe = GOE_sampler(self.order, self.n)
+        chi2 = None
         if isinstance(measure, MaternSpectralMeasure):
-            nu, lengthscale = measure.nu[0], measure.lengthscale[0]
-            scale = 1 / torch.sqrt((self.n ** 3 - self.n) / 48 + 2 * nu / lengthscale)
-            goe = GOE_sampler(self.order, self.n)
-            chi2 = torch.distributions.chi2.Chi2(2 * nu).rsample((self.order,))
-            lmd = goe / torch.sqrt(chi2)[:, None] / scale
-        elif isinstance(measure, SqExpSpectralMeasure):
-            lmd = GOE_sampler(self.order, self.n) / measure.lengthscale
-        else:
+            chi2 = torch.distributions.chi2.Chi2(2 * measure.nu[0]).rsample((self.order,))
+        return shift, goe, chi2
+
+    def _inverse_scale(self, measure):
+        """lmd = base * this: sqrt((n^3 - n) / 48 + 2 nu / l) for Matern (spd.py:31: l, not l^2), 1 / l for the heat kernel."""
+        if isinstance(measure, MaternSpectralMeasure):
+            return torch.sqrt((self.n ** 3 - self.n) / 48 + 2 * measure.nu[0] / measure.lengthscale[0])
+        return 1.0 / measure.lengthscale[0]
+
+    def generate_lb_eigenspaces(self, measure):
+        if not isinstance(measure, (MaternSpectralMeasure, SqExpSpectralMeasure)):
             return NotImplementedError
+        shift, goe, chi2 = self._draw(measure)
+        if chi2 is not None:
+            scale = 1 / torch.sqrt((self.n ** 3 - self.n) / 48 + 2 * measure.nu[0] / measure.lengthscale[0])
+            lmd = goe / torch.sqrt(chi2)[:, None] / scale
+        else:
+            lmd = goe / measure.lengthscale
         lmd = lmd.detach()
+        self._base_lmd = None
         self.lb_eigenspaces = _SphericalFunctions(lmd, shift, self, self.c_function_tanh(lmd))
+
+    def _differentiable_spectrum(self, measure, resample):
+        """(lmd [m, n], shift, coeff) with lmd and coeff attached to the autograd graph of the lengthscale.  resample: new
+        shifts and spectra as `generate_lb_eigenspaces` draws them on every training-mode forward (spd.py:28)."""
+        inv_scale = self._inverse_scale(measure)
+        if resample:
+            shift, goe, chi2 = self._draw(measure)
+            base = goe if chi2 is None else goe / torch.sqrt(chi2)[:, None]
+            lmd = base.detach() * inv_scale
+        else:
+            shift = self.lb_eigenspaces.exp.shift
+            lmd = self.lb_eigenspaces.exp.lmd.detach() * (inv_scale / inv_scale.detach())
+        return lmd, shift, self.c_function_tanh(lmd)
+
+    def _log_terms(self, x, funcs):
+        """la[i, k, r] = log a_r(U_i h_k^{-1}): dF_ik / dlmd_kr = i la_r F_ik  (CUDA kernel `lsk_spd_logdiag`)"""
+        lib = _lib.load()
+        u = self.to_group(x).to(dtype).contiguous()
+        hinv = self.inv(funcs.exp.shift)
+        m = funcs.exp.lmd.shape[0]
+        out = torch.empty((u.shape[0], m, self.n), dtype=dtype, device=u.device)
+        if u.shape[0] and m:
+            _lib.check(lib.lsk_spd_logdiag(_lib.ptr(u), _lib.ptr(hinv), u.shape[0], m, self.n, _lib.ptr(out), _lib.stream_ptr()),
+                       "lsk_spd_logdiag")
+            _lib.count_launch()
+        return out
 
     def c_function_tanh(self, lmd):
         """spd.py:116-123"""

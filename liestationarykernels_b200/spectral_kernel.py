@@ -275,26 +275,15 @@ class RandomFourierFeatureKernel(AbstractSpectralKernel):
             self.normalizer = self.forward(point, point, normalize=False)[0, 0]
 
     def _differentiable(self, x, y, normalize):
-        """Hyperbolic space: forward with lengthscale / variance gradients.  The spectral samples move with the lengthscale
-        (lmd = normalised samples * scale(l), hyperbolic.py:43-52) and the c-function with them; both stay torch functions
-        of the parameters on the host, the N * M * m work of forward and backward runs on the feature and tile kernels
-        (`lazy._HypGramFn`).  Same state side effects as the plain path (features regenerated, normaliser recomputed)."""
+        """Forward with lengthscale / variance gradients.  The spectral samples move with the lengthscale (lmd = samples *
+        scale(l), hyperbolic.py:43-52, spd.py:27-43) and the c-function with them; both stay torch functions of the parameters
+        on the host, the N * M * m work of forward and backward runs on the feature and tile kernels (`lazy._FourierGramFn`).
+        Same state side effects as the plain path (training mode: features regenerated, normaliser recomputed)."""
         from .lazy import DifferentiableFourierGram
         from .spaces.noncompact import _SphericalFunctions
-        from .spectral_measure import MaternSpectralMeasure
         m, meas = self.manifold, self.measure
-        if m.normalized_lmd is None:
-            m._generate_lb_eigenspace(meas)
-        if isinstance(meas, MaternSpectralMeasure):
-            scale = torch.sqrt(1 / 4 + 2 * meas.nu[0] / (meas.lengthscale[0] ** 2))
-        else:
-            scale = 1.0 / torch.abs(meas.lengthscale[0])
-        if self.training:
-            lmd = m.normalized_lmd.detach() * scale
-        else:           # eval mode keeps the features of the last generate_lb_eigenspaces call; gradients still flow via scale
-            lmd = m.lb_eigenspaces.exp.lmd.detach() / scale.detach() * scale
-        coeff = m.c_function(lmd)
-        funcs = _SphericalFunctions(lmd.detach(), m.shift if self.training else m.lb_eigenspaces.exp.shift, m, coeff.detach())
+        lmd, shift, coeff = m._differentiable_spectrum(meas, resample=self.training)
+        funcs = _SphericalFunctions(lmd.detach(), shift, m, coeff.detach())
         if self.training:
             m.lb_eigenspaces = funcs
         if normalize:
@@ -311,7 +300,7 @@ class RandomFourierFeatureKernel(AbstractSpectralKernel):
     def forward(self, x, y=None, normalize=True):
         if y is None:
             y = x
-        if torch.is_grad_enabled() and hasattr(self.manifold, "normalized_lmd") and \
+        if torch.is_grad_enabled() and hasattr(self.manifold, "_differentiable_spectrum") and \
                 (self.measure.lengthscale.requires_grad or self.measure.variance.requires_grad):
             return self._differentiable(x, y, normalize)
         if self.training:

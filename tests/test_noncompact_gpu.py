@@ -126,3 +126,48 @@ def test_hyperbolic_fourier_kernel_hyperparameter_gradients(kind, n, m):
     with torch.no_grad():
         plain = kern(x.cuda()).evaluate()
     assert kxx.requires_grad and scaled_err(kxx.detach().cpu(), plain.cpu()) < 1e-13
+
+
+@pytest.mark.parametrize("kind,n,m,training", [("matern", 3, 40, True), ("heat", 2, 32, True), ("matern", 2, 24, False)])
+def test_spd_fourier_kernel_hyperparameter_gradients(kind, n, m, training):
+    """RandomFourierFeatureKernel on SPD(n): value and lengthscale / variance gradients against torch autograd through the
+    oracle port.  SPD re-draws shifts and spectra on every training-mode forward (spd.py:28): the oracle's draws are injected
+    through `space._draw` (same-tensor rule).  Eval mode: stored features and normaliser, gradient through the scale only."""
+    import lsk_oracle as orc
+    from liestationarykernels_b200.spaces import SymmetricPositiveDefiniteMatrices
+    from liestationarykernels_b200.spectral_kernel import RandomFourierFeatureKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure, SqExpSpectralMeasure
+    torch.manual_seed(29)
+    os_ = orc.SPD(n, order=m)
+    om = orc.Measure(kind, os_.dim, 0.9, 1.5 if kind == "matern" else None, 1.4)
+    nx, ny = 21, 17
+    x, y = os_.rand(nx), os_.rand(ny)
+    # raw draws in the reference's order, then lmd as a differentiable function of the lengthscale
+    shift = os_.rand_phase(m)
+    goe = orc.goe_spectrum(m, n)
+    chi2 = torch.distributions.chi2.Chi2(2 * om.nu[0]).rsample((m,)) if kind == "matern" else None
+    om.lengthscale.requires_grad_(True)
+    om.variance.requires_grad_(True)
+    if kind == "matern":
+        scale = 1 / torch.sqrt((n ** 3 - n) / 48 + 2 * om.nu[0] / om.lengthscale[0])
+        lmd = goe / torch.sqrt(chi2)[:, None] / scale
+    else:
+        lmd = goe / om.lengthscale
+    norm = orc.rff_normalizer(os_, lmd, shift)
+    if not training:
+        norm = norm.detach()
+    k_ref = orc.rff_kernel(os_, om, lmd, shift, x, y, norm)
+    g_out = torch.randn(nx, ny, dtype=torch.float64)
+    (k_ref * g_out).sum().backward()
+    space = SymmetricPositiveDefiniteMatrices(n, order=m)
+    space._draw = lambda measure: (shift.cuda(), goe.cuda(), None if chi2 is None else chi2.cuda())
+    meas = MaternSpectralMeasure(os_.dim, 0.9, 1.5, 1.4) if kind == "matern" else SqExpSpectralMeasure(os_.dim, 0.9, 1.4)
+    kern = RandomFourierFeatureKernel(meas, space)
+    kern.train(training)
+    k = kern(x.cuda(), y.cuda()).evaluate()
+    assert scaled_err(k.detach().cpu(), k_ref.detach()) < 1e-10
+    assert abs(float(kern.normalizer) - norm.item()) < 1e-10 * abs(norm.item())
+    (k * g_out.cuda()).sum().backward()
+    for ours, ref in ((meas.lengthscale.grad, om.lengthscale.grad), (meas.variance.grad, om.variance.grad)):
+        assert ours is not None
+        assert abs(ours.item() - ref.item()) < 1e-8 * max(1.0, abs(ref.item())), (ours.item(), ref.item())
