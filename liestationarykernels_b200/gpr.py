@@ -7,7 +7,12 @@ the number of targets, Adam + StepLR.
 The marginal likelihood and the posterior run on this package's fp64 Cholesky (`linalg.CholeskyFactor` ->
 `lsk_potrf_upper` / `lsk_potrs_upper` / `lsk_potri_upper`, csrc/lsk_cholesky.cu).  Hyper-parameter gradients flow through
 `EigenbasisSumKernel`'s fused backward (spectral_kernel._WeightedCharacterSum); the gradient of the log-determinant needs
-the dense inverse (`CholeskyFactor.inverse`)."""
+the dense inverse (`CholeskyFactor.inverse`).
+
+One deliberate difference from gpytorch: inside an autograd graph the diagonal shifts (`+ 1e-6 I`, `+ noise I`) are applied
+IN PLACE to the covariance the kernel just produced (an N x N identity and two extra passes per shift otherwise), so
+`output.covariance_matrix` of a training-mode `model(x)` holds the shifted matrix after `mll(output, y)` was evaluated.
+Tensors outside a graph (eval mode, `torch.no_grad()`) are never modified."""
 from __future__ import annotations
 
 import math
@@ -41,12 +46,36 @@ class _GaussianLogProb(torch.autograd.Function):
         f, alpha = ctx.factor, ctx.alpha
         grad_covar = grad_resid = None
         if ctx.needs_input_grad[0]:
-            grad_covar = f.inverse().mul_(-0.5)
-            grad_covar.addr_(alpha, alpha, alpha=0.5)
-            grad_covar.mul_(g)
+            gs = float(g)
+            grad_covar = f.inverse().addr_(alpha, alpha, beta=-0.5 * gs, alpha=0.5 * gs)     # one pass over the N x N inverse
         if ctx.needs_input_grad[1]:
             grad_resid = -g * alpha
         return grad_covar, grad_resid
+
+
+class _AddToDiagonal(torch.autograd.Function):
+    """covar + shift * I, written into covar itself when this module owns the buffer (the kernel's fresh output): the
+    reference's `K + 1e-6 * eye` and the likelihood's `+ noise * eye` each cost an N x N identity plus two passes over the
+    matrix otherwise.  Gradients: identity for covar, trace for shift."""
+
+    @staticmethod
+    def forward(ctx, covar, shift):
+        ctx.mark_dirty(covar)
+        covar.diagonal().add_(shift.reshape(()) if isinstance(shift, torch.Tensor) else shift)
+        return covar
+
+    @staticmethod
+    def backward(ctx, grad):
+        g_shift = torch.diagonal(grad).sum().reshape(1) if ctx.needs_input_grad[1] else None
+        return grad, g_shift
+
+
+def _add_to_diagonal(covar, shift):
+    """covar + shift * I; in place when covar is a non-leaf tensor nobody else holds (our kernels' outputs), else a copy."""
+    shift_t = shift if isinstance(shift, torch.Tensor) else torch.tensor([shift], dtype=dtype, device=covar.device)
+    if covar.is_leaf or covar.stride(1) != 1:
+        covar = covar.clone()
+    return _AddToDiagonal.apply(covar, shift_t)
 
 
 class MultivariateNormal:
@@ -82,9 +111,7 @@ class GaussianLikelihood(torch.nn.Module):
         return torch.nn.functional.softplus(self.raw_noise) + 1e-4
 
     def forward(self, dist: MultivariateNormal) -> MultivariateNormal:
-        n = dist.mean.shape[0]
-        eye = torch.eye(n, dtype=dtype, device=dist.mean.device)
-        return MultivariateNormal(dist.mean, dist.covariance_matrix + self.noise * eye)
+        return MultivariateNormal(dist.mean, _add_to_diagonal(dist.covariance_matrix, self.noise))
 
 
 class ConstantMean(torch.nn.Module):
@@ -119,8 +146,7 @@ class ExactGPModel(torch.nn.Module):
 
     def forward(self, x):
         mean_x = self.mean_module(x)
-        covar_x = _dense(self.covar_module(self._points(x)))
-        covar_x = covar_x + 1e-6 * torch.eye(x.shape[0], device=covar_x.device, dtype=dtype)
+        covar_x = _add_to_diagonal(_dense(self.covar_module(self._points(x))), 1e-6)
         return MultivariateNormal(mean_x, covar_x)
 
     def train(self, mode=True):

@@ -73,7 +73,7 @@ class _WeightedCharacterSum(torch.autograd.Function):
                 _, tangent = torch.func.jvp(f, (params[i].detach(),), (torch.ones_like(params[i]),))
             with torch.no_grad():
                 dk = kernel._evaluate(ctx.x, ctx.y, tangent.detach().cpu().numpy(), None)
-                grads.append((grad * dk).sum().reshape(params[i].shape))
+                grads.append(torch.dot(grad.reshape(-1), dk.reshape(-1)).reshape(params[i].shape))    # one pass, no N x M temporary
         return (None, None, None, None, None, *grads)
 
 
