@@ -80,6 +80,10 @@ typedef struct LskEpilogue {
 
 int lsk_version(void);
 
+/* Text for a return code of any entry point (0 ok, < 0 LSK_E*, > 0 cudaError_t).  Stateless: the library keeps no
+ * "last error"; every call reports through its return value. */
+const char* lsk_error_string(int code);
+
 /* Number of doubles of the panel-major embedding buffer for `num` points and `kg_total` k-groups. */
 long long lsk_embed_buffer_doubles(long long num, int kg_total);
 

@@ -52,6 +52,7 @@ _lib = None
 
 _PROTOTYPES = {
     "lsk_version": (ctypes.c_int, []),
+    "lsk_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "lsk_embed_buffer_doubles": (ctypes.c_longlong, [ctypes.c_longlong, ctypes.c_int]),
     "lsk_embed_points": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
@@ -130,10 +131,8 @@ def require_cuda():
 def check(code: int, what: str):
     if code == 0:
         return
-    if code < 0:
-        names = {-1: "invalid argument", -2: "size out of range", -3: "unsupported configuration"}
-        raise LskError("%s: %s (code %d)" % (what, names.get(code, "argument error"), code))
-    raise LskError("%s: CUDA error %d" % (what, code))
+    text = load().lsk_error_string(int(code))
+    raise LskError("%s: %s (code %d)" % (what, text.decode() if text else "error", code))
 
 
 def stream_ptr():

@@ -435,6 +435,17 @@ extern "C" int lsk_embed_points2(const void* x, long long num_x, const int* part
 
 extern "C" int lsk_version(void) { return LSK_VERSION; }
 
+// Stateless: the text for a return code of any entry point (0 ok, < 0 LSK_E*, > 0 cudaError_t).
+extern "C" const char* lsk_error_string(int code) {
+    switch (code) {
+    case 0: return "ok";
+    case LSK_EARG: return "invalid argument";
+    case LSK_ESIZE: return "size out of supported range";
+    case LSK_EUNSUPPORTED: return "configuration not compiled";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error code";
+    }
+}
+
 extern "C" long long lsk_embed_buffer_doubles(long long num, int kg_total) {
     return ((num + lsk::ROW_PAD - 1) / lsk::ROW_PAD) * (lsk::ROW_PAD / lsk::PANEL) * (long long)kg_total * (lsk::PANEL * 4);
 }
