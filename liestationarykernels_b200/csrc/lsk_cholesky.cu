@@ -1,17 +1,22 @@
-// Blocked fp64 Cholesky factorisation and triangular solves for the GP regression step that consumes the covariance
+// Blocked fp64 Cholesky factorisation, triangular solves and inverse for the GP regression step that consumes the covariance
 // (the reference hands K + sigma_n^2 I to gpytorch's ExactGP, examples/gpr_model.py:26-39, whose
-// marginal likelihood / prediction is a LAPACK/cuSOLVER potrf + potrs).
+// marginal likelihood / prediction is a LAPACK/cuSOLVER potrf + potrs, and whose gradient needs tr(K^{-1} dK)).
 //
 //   A = U^T U,  U upper triangular, factorised IN PLACE in the upper triangle of a row-major matrix (equivalently: the
-//   lower factor L = U^T of the same matrix read column-major).  Right-looking, block size 128:
+//   lower factor L = U^T of the same matrix read column-major).  Right-looking, 128-column panels, two panels per
+//   trailing update (lsk_potrf_upper):
 //     diag_kernel   one CTA: U_kk = chol(A_kk) and W_kk = U_kk^{-1}, both register-resident rank-1 sweeps (each thread owns
 //                   a cyclic 4 x 8 sub-block; one row broadcast through shared memory and ONE barrier per step)
 //     trsm_kernel   row panel U_k,: = W_kk^T A_k,: on the fp64 tensor-core path (DMMA), written twice: row-major into A
 //                   (the factor) and panel-major into the workspace (the operand layout of the pairwise kernel)
-//     pairwise_kernel<SYRK>  trailing update A_ij -= U_ki^T U_kj on the tiles that reach the diagonal or lie above it
-//                   (lsk_pairwise.cu: TMA ring + DMMA, read-modify-write epilogue)
-//   The inverses W_kk stay in the workspace: the triangular solves U^T y = b, U x = y are then one small matrix-vector
-//   product per block plus a panel update (fwd_step_kernel / bwd_step_kernel), no divisions, no dependent chains.
+//     pairwise_kernel<SYRK>  strip / trailing update A_ij -= U_ki^T U_kj (K = 128 / 256) on the tiles that reach the
+//                   diagonal or lie above it (lsk_pairwise.cu: TMA ring + DMMA, read-modify-write epilogue)
+//   The inverses W_kk stay in the workspace:
+//     lsk_potrs_upper  U^T y = b, U x = y: one 128 x 128 matrix-vector product per block plus a panel update
+//                      (fwd_step_kernel / bwd_step_kernel), no divisions, no dependent chains
+//     lsk_trsm_lower   the forward solve for a block of right-hand sides (trsm_kernel + repack_kernel + tile kernel)
+//     lsk_potri_upper  Y = U^{-T} by the same sweep on the identity and A^{-1} = sum_k Y_k^T Y_k on the triangular tile
+//                      schedule: 2 n^3 / 3 flop, the zero structure of U^{-T} used exactly at block level
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
 
