@@ -113,7 +113,11 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host core
     block = {"so5": (16, 16), "so3": (256, 256), "su4": (96, 96)}[args.workload]
+    if args.workload == "so5":                       # ~50 entries/s: keep the whole run near two minutes for any --steps
+        side = max(6, min(16, int((5000.0 / max(args.steps, 1)) ** 0.5)))
+        block = (side, side)
     for _ in range(min(args.warmup, 1)):
         oracle_block(args.workload, block[0] // 2, block[1] // 2)
     total_t, total_e = 0.0, 0
