@@ -49,7 +49,9 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // ------------------------------------------------------------------------------------------------------------
 // diagonal block
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
+constexpr int DIAG_THREADS = 256;
+
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __restrict__ Wg, int* __restrict__ info)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -58,29 +60,33 @@ diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __res
     double* dpiv = rowbuf + 2 * NB;                           // pivots d_j (= U_jj^2)
     double* udiag = dpiv + NB;                                // U_jj
     double* uinv = udiag + NB;                                // 1 / U_jj
-    const int t = threadIdx.x, tr = t >> 4, tc = t & 15;      // thread owns rows tr + 32 i, columns tc + 16 k (cyclic)
+    // 256 threads, each owns an 8 x 8 cyclic sub-block: rows tr + 16 i, columns tc + 16 k.  (A 4 x 8 block on 512 threads
+    // needs 12 shared-memory reads per 32 multiply-adds and twice the warps at every barrier: 66 us per block against 40.)
+    const int t = threadIdx.x, tr = t >> 4, tc = t & 15;
 
-    double a[4][8];
+    double a[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int r = tr + 32 * i, c = tc + 16 * k;
+            const int r = tr + 16 * i, c = tc + 16 * k;
             double v = (r == c) ? 1.0 : 0.0;                  // identity padding of a ragged last block
             if (r < nb && c < nb) v = (c >= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0;
             a[i][k] = v;
         }
 
-    // ---- phase 1: right-looking elimination.  After step j, row j holds d_j^{1/2}-unscaled U: U[j][c] = a[j][c] / sqrt(d_j)
+    // ---- phase 1: right-looking elimination.  After step j, row j holds the unscaled U: U[j][c] = a[j][c] / sqrt(d_j).
+    // Only entries that can lie on or above the diagonal are kept up to date: column group k reaches row group i iff
+    // k >= i; rows <= j are final (i < jb).
 #pragma unroll
-    for (int jb = 0; jb < 4; ++jb) {
+    for (int jb = 0; jb < 8; ++jb) {
 #pragma unroll 1
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = 32 * jb + jj;
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * jb + jj;
             double* buf = rowbuf + (j & 1) * NB;
             if (tr == jj) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) buf[tc + 16 * k] = a[jb][k];
+                for (int k = 0; k < 8; ++k) if (k >= jb) buf[tc + 16 * k] = a[jb][k];
             }
             __syncthreads();
             const double d = buf[j];
@@ -89,18 +95,16 @@ diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __res
                 if (!(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);   // not positive definite (LAPACK info convention)
             }
             const double id = fast_rcp(d);
-            // only entries that can lie on or above the diagonal are kept up to date: column group k reaches row group i
-            // iff k >= 2 i (columns tc + 16 k, rows tr + 32 i); rows <= j are final (i < jb)
             double vc[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (k >= 2 * jb) vc[k] = buf[tc + 16 * k];
+            for (int k = 0; k < 8; ++k) if (k >= jb) vc[k] = buf[tc + 16 * k];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 if (i < jb) continue;
-                const int r = tr + 32 * i;
+                const int r = tr + 16 * i;
                 const double vr = (r > j) ? buf[r] * id : 0.0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) if (k >= 2 * i) a[i][k] = fma(-vr, vc[k], a[i][k]);
+                for (int k = 0; k < 8; ++k) if (k >= i) a[i][k] = fma(-vr, vc[k], a[i][k]);
             }
         }
     }
@@ -113,10 +117,10 @@ diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __res
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int r = tr + 32 * i, c = tc + 16 * k;
+            const int r = tr + 16 * i, c = tc + 16 * k;
             if (c >= r) {
                 const double u = (c == r) ? udiag[r] : a[i][k] * uinv[r];
                 S[r * SLD + c] = u;
@@ -125,41 +129,41 @@ diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __res
         }
     __syncthreads();
 
-    // ---- phase 2: B = U^{-T} by the same sweep applied to the identity:  B[j][:] /= U_jj;  B[r][:] -= U[j][r] B[j][:], r > j
-    double b[4][8];
+    // ---- phase 2: B = U^{-T} by the same sweep applied to the identity:  B[j][:] /= U_jj;  B[r][:] -= U[j][r] B[j][:], r > j.
+    // Row j of B vanishes right of column j: only column groups k <= jb carry anything.  `a` is dead: its registers are reused.
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) b[i][k] = (tr + 32 * i == tc + 16 * k) ? 1.0 : 0.0;
+        for (int k = 0; k < 8; ++k) a[i][k] = (tr + 16 * i == tc + 16 * k) ? 1.0 : 0.0;
 #pragma unroll
-    for (int jb = 0; jb < 4; ++jb) {
+    for (int jb = 0; jb < 8; ++jb) {
 #pragma unroll 1
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = 32 * jb + jj;
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * jb + jj;
             double* buf = rowbuf + (j & 1) * NB;
             if (tr == jj) {
                 const double s = uinv[j];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) if (k <= 2 * jb + 1) { b[jb][k] *= s; buf[tc + 16 * k] = b[jb][k]; }
+                for (int k = 0; k < 8; ++k) if (k <= jb) { a[jb][k] *= s; buf[tc + 16 * k] = a[jb][k]; }
             }
             __syncthreads();
-            double vc[8];                                      // row j of B vanishes right of column j: k <= 2 jb + 1
+            double vc[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (k <= 2 * jb + 1) vc[k] = buf[tc + 16 * k];
+            for (int k = 0; k < 8; ++k) if (k <= jb) vc[k] = buf[tc + 16 * k];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 if (i < jb) continue;
-                const int r = tr + 32 * i;
+                const int r = tr + 16 * i;
                 const double ur = (r > j) ? S[j * SLD + r] : 0.0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) if (k <= 2 * jb + 1) b[i][k] = fma(-ur, vc[k], b[i][k]);
+                for (int k = 0; k < 8; ++k) if (k <= jb) a[i][k] = fma(-ur, vc[k], a[i][k]);
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) Wg[wg_index(tr + 32 * i, tc + 16 * k)] = b[i][k];
+        for (int k = 0; k < 8; ++k) Wg[wg_index(tr + 16 * i, tc + 16 * k)] = a[i][k];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -418,7 +422,7 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
     for (long long k0 = 0, blk = 0; k0 < n; k0 += 2 * NB, blk += 2) {
         // ---- first panel
         const int nb1 = (int)((n - k0) < NB ? (n - k0) : NB);
-        diag_kernel<<<1, 512, DIAG_SMEM, st>>>(A, lda, (int)k0, nb1, W + blk * WBLK, info);
+        diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, lda, (int)k0, nb1, W + blk * WBLK, info);
         const long long s1 = k0 + NB, m1 = n - s1;
         if (m1 <= 0) break;
         trsm_kernel<<<(unsigned)(((m1 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, s1, n, (int)k0, W + blk * WBLK, P, KG2, 0);
@@ -429,7 +433,7 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
         int rc = lsk_pairwise_poly(P, P, strip, m1, KG2, &ep, A + s1 * lda + s1, lda, stream);
         if (rc != 0) return rc;
         // ---- second panel
-        diag_kernel<<<1, 512, DIAG_SMEM, st>>>(A, lda, (int)s1, (int)strip, W + (blk + 1) * WBLK, info);
+        diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, lda, (int)s1, (int)strip, W + (blk + 1) * WBLK, info);
         const long long s2 = s1 + NB, m2 = n - s2;
         if (m2 <= 0) break;
         double* P2 = P + 2ll * KG2 * 256;                // operand rows are relative to s2: two 64-row panels further
