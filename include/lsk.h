@@ -196,7 +196,7 @@ long long lsk_potrf_work_doubles(long long n);
 int lsk_potrf_upper(void* A, long long n, long long lda, void* work, void* info_dev, void* stream);
 
 /* Triangular solves with the factor and workspace of lsk_potrf_upper, one right-hand side, in place in b [n]:
- * which = 1: U^T y = b;  2: U x = b;  3: both (A x = b, LAPACK dpotrs).  tmp: device scratch, n doubles. */
+ * which = 1: U^T y = b;  2: U x = b;  3: both (A x = b, LAPACK dpotrs).  tmp: device scratch, n + 128 doubles. */
 int lsk_potrs_upper(const void* U, long long n, long long lda, const void* work, void* b, void* tmp, int which, void* stream);
 
 /* Forward substitution with many right-hand sides, in place: B [n, nrhs] (row-major, ldb) <- U^{-T} B = L^{-1} B — the

@@ -13,7 +13,7 @@
 //                   diagonal or lie above it (lsk_pairwise.cu: TMA ring + DMMA, read-modify-write epilogue)
 //   The inverses W_kk stay in the workspace:
 //     lsk_potrs_upper  U^T y = b, U x = y: one 128 x 128 matrix-vector product per block plus a panel update
-//                      (fwd_step_kernel / bwd_step_kernel), no divisions, no dependent chains
+//                      (block_matvec_kernel + fwd/bwd_update_kernel), no divisions, no dependent chains
 //     lsk_trsm_lower   the forward solve for a block of right-hand sides (trsm_kernel + repack_kernel + tile kernel)
 //     lsk_potri_upper  Y = U^{-T} by the same sweep on the identity and A^{-1} = sum_k Y_k^T Y_k on the triangular tile
 //                      schedule: 2 n^3 / 3 flop, the zero structure of U^{-T} used exactly at block level
@@ -249,27 +249,53 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n_rows, long long c
 // ------------------------------------------------------------------------------------------------------------
 // triangular solves with one right-hand side, one launch per block
 // ------------------------------------------------------------------------------------------------------------
-// forward (U^T y = b):  y_k = B r_k;  r_j -= U[k-rows, j]^T y_k for the columns j behind the block.
-// CTA = 64 columns x 4 slices of the block's rows (32 each), reduced through shared memory.
-__global__ void __launch_bounds__(256)
-fwd_step_kernel(const double* __restrict__ U, long long lda, long long n, int k0, int nb, const double* __restrict__ Wg,
-                double* __restrict__ r, double* __restrict__ y)
+// Block step of the triangular solves, two launches:
+//   block_matvec_kernel (one CTA)   z = B r_k (forward, B = U_kk^{-T}) or z = B^T r_k (backward); z is the solution block
+//   fwd_update_kernel               r_j -= U[k-rows, j]^T z   for the columns j behind the block
+//   bwd_update_kernel               r_i -= U[i, k-cols] z     for the rows i above the block
+// (One fused launch per block made every CTA repeat the 128 x 128 matrix-vector product: 256 CTAs x 128 KB through L2 per
+// step, 26 us per block; split: 11 us.)
+__global__ void __launch_bounds__(512)
+block_matvec_kernel(const double* __restrict__ Wg, const double* __restrict__ r, int k0, int nb, int transpose,
+                    double* __restrict__ z_out /* [128] scratch */, double* __restrict__ sol /* solution vector */)
 {
-    __shared__ double rk[NB], z[NB], part[4][64];
+    __shared__ double rk[NB];
     const int t = threadIdx.x;
+    pdl_launch_dependents();                         // the next launch of the chain may become resident now ...
+    pdl_wait();                                      // ... and, like this one, waits here for its predecessor to finish
     if (t < NB) rk[t] = t < nb ? r[k0 + t] : 0.0;
     __syncthreads();
-    if (t < NB) {
-        double acc0 = 0.0, acc1 = 0.0;
-        for (int g = 0; g <= (t >> 2); ++g) {
-            const double2* w = reinterpret_cast<const double2*>(Wg + g * (NB * 4) + t * 4);
+    const int row = t >> 2, sub = t & 3;             // four threads per output entry
+    double acc = 0.0;
+    if (!transpose) {                                // z[kk] = sum_{q <= kk} B[kk][q] r[q]; k-groups g = sub, sub + 4, ...
+        for (int g = sub; g <= (row >> 2); g += 4) {
+            const double2* w = reinterpret_cast<const double2*>(Wg + g * (NB * 4) + row * 4);
             const double2 w0 = w[0], w1 = w[1];
-            acc0 = fma(w0.x, rk[4 * g], acc0); acc1 = fma(w0.y, rk[4 * g + 1], acc1);
-            acc0 = fma(w1.x, rk[4 * g + 2], acc0); acc1 = fma(w1.y, rk[4 * g + 3], acc1);
+            acc = fma(w0.x, rk[4 * g], acc); acc = fma(w0.y, rk[4 * g + 1], acc);
+            acc = fma(w1.x, rk[4 * g + 2], acc); acc = fma(w1.y, rk[4 * g + 3], acc);
         }
-        z[t] = acc0 + acc1;
-        if (blockIdx.x == 0 && t < nb) y[k0 + t] = acc0 + acc1;
+    } else {                                         // z[q] = sum_{kk >= q} B[kk][q] r[kk]
+        const double* w = Wg + (row >> 2) * (NB * 4) + (row & 3);
+        for (int kk = row + sub; kk < NB; kk += 4) acc = fma(w[kk * 4], rk[kk], acc);
     }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (sub == 0) {
+        z_out[row] = acc;
+        if (row < nb) sol[k0 + row] = acc;
+    }
+}
+
+// CTA = 64 columns x 4 slices of the block's rows (32 each), reduced through shared memory.
+__global__ void __launch_bounds__(256)
+fwd_update_kernel(const double* __restrict__ U, long long lda, long long n, int k0, int nb, const double* __restrict__ zg,
+                  double* __restrict__ r)
+{
+    __shared__ double z[NB], part[4][64];
+    const int t = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (t < NB) z[t] = zg[t];
     __syncthreads();
     const int tx = t & 63, ty = t >> 6;
     const long long j = (long long)k0 + nb + 64ll * blockIdx.x + tx;
@@ -293,25 +319,15 @@ fwd_step_kernel(const double* __restrict__ U, long long lda, long long n, int k0
     if (ty == 0 && j < n) r[j] -= (part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx]);
 }
 
-// backward (U x = y):  x_k = B^T r_k;  r_i -= U[i, k-cols] x_k for the rows i above the block.
 // CTA = 64 rows, 4 threads per row (32 contiguous doubles each), reduced by shuffles.
 __global__ void __launch_bounds__(256)
-bwd_step_kernel(const double* __restrict__ U, long long lda, long long n, int k0, int nb, const double* __restrict__ Wg,
-                double* __restrict__ r, double* __restrict__ x)
+bwd_update_kernel(const double* __restrict__ U, long long lda, int k0, int nb, const double* __restrict__ zg, double* __restrict__ r)
 {
-    __shared__ double rk[NB], z[NB];
+    __shared__ double z[NB];
     const int t = threadIdx.x;
-    if (t < NB) rk[t] = t < nb ? r[k0 + t] : 0.0;
-    __syncthreads();
-    if (t < NB) {
-        double acc0 = 0.0, acc1 = 0.0;                      // z[q] = sum_{kk >= q} B[kk][q] r[kk]
-        const double* w = Wg + (t >> 2) * (NB * 4) + (t & 3);
-        int kk = t;
-        for (; kk + 1 < NB; kk += 2) { acc0 = fma(w[kk * 4], rk[kk], acc0); acc1 = fma(w[kk * 4 + 4], rk[kk + 1], acc1); }
-        if (kk < NB) acc0 = fma(w[kk * 4], rk[kk], acc0);
-        z[t] = acc0 + acc1;
-        if (blockIdx.x == 0 && t < nb) x[k0 + t] = acc0 + acc1;
-    }
+    pdl_launch_dependents();
+    pdl_wait();
+    if (t < NB) z[t] = zg[t];
     __syncthreads();
     const int sub = t & 3;
     const long long i = 64ll * blockIdx.x + (t >> 2);
@@ -448,9 +464,10 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
 }
 
 // which: 1 = forward only (U^T y = b), 2 = backward only (U x = b), 3 = both (U^T U x = b).  `b` is overwritten with the
-// solution; `tmp` is an n-double scratch vector.
+// solution; `tmp` is a scratch vector of n + 128 doubles.
 extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const void* work_, void* b_, void* tmp_, int which,
                                void* stream) {
+    using namespace lsk;
     using namespace lsk::chol;
     if (!U_ || !work_ || !b_ || !tmp_) return LSK_EARG;
     if (n < 0 || lda < n || n > 0x7fffffffLL) return LSK_ESIZE;
@@ -464,13 +481,14 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
     const long long nblk = n_blocks(n);
     double* cur = b;      // residual vector that is consumed
     double* oth = tmp;    // solution vector that is produced
+    double* zbuf = tmp + n;                                         // the 128 doubles behind the caller's scratch vector
     if (which & 1) {
         for (long long blk = 0; blk < nblk; ++blk) {
             const long long k0 = blk * NB;
             const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
             const long long m = n - k0 - nb;
-            const unsigned grid = (unsigned)(m > 0 ? (m + 63) / 64 : 1);
-            fwd_step_kernel<<<grid, 256, 0, st>>>(U, lda, n, (int)k0, nb, W + blk * WBLK, cur, oth);
+            launch_pdl(block_matvec_kernel, dim3(1), dim3(512), 0, st, W + blk * WBLK, (const double*)cur, (int)k0, nb, 0, zbuf, oth);
+            if (m > 0) launch_pdl(fwd_update_kernel, dim3((unsigned)((m + 63) / 64)), dim3(256), 0, st, U, lda, n, (int)k0, nb, (const double*)zbuf, cur);
         }
         double* sw = cur; cur = oth; oth = sw;
     }
@@ -478,8 +496,8 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
         for (long long blk = nblk - 1; blk >= 0; --blk) {
             const long long k0 = blk * NB;
             const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
-            const unsigned grid = (unsigned)(k0 > 0 ? (k0 + 63) / 64 : 1);
-            bwd_step_kernel<<<grid, 256, 0, st>>>(U, lda, n, (int)k0, nb, W + blk * WBLK, cur, oth);
+            launch_pdl(block_matvec_kernel, dim3(1), dim3(512), 0, st, W + blk * WBLK, (const double*)cur, (int)k0, nb, 1, zbuf, oth);
+            if (k0 > 0) launch_pdl(bwd_update_kernel, dim3((unsigned)((k0 + 63) / 64)), dim3(256), 0, st, U, lda, (int)k0, nb, (const double*)zbuf, cur);
         }
         double* sw = cur; cur = oth; oth = sw;
     }

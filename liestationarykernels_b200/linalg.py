@@ -66,7 +66,7 @@ class CholeskyFactor:
             raise ValueError("right-hand side must be [n] or [n, k] with n = %d" % self.n)
         vec = b.dim() == 1
         cols = b.to(F64).reshape(self.n, -1).t().contiguous().clone()      # [k, n]: one contiguous vector per column
-        tmp = torch.empty(max(self.n, 1), dtype=F64, device=self.matrix.device)
+        tmp = torch.empty(self.n + 128, dtype=F64, device=self.matrix.device)
         blocks = (self.n + 127) // 128
         for c in range(cols.shape[0] if self.n else 0):
             _lib.check(lib.lsk_potrs_upper(_lib.ptr(self.matrix), self.n, self.matrix.stride(0),
