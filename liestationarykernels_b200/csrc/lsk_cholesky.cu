@@ -193,15 +193,23 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n_rows, long long c
         for (int c = 0; c < 4; ++c) bulk_g2s(sW + c * (WBLK / 4), Wg + c * (WBLK / 4), (WBLK / 4) * 8, bar);
     }
     {
+        // all 32 loads of a thread are issued before the first store: the panel comes from HBM and this kernel is on the
+        // serial path of the factorisation (with the loads consumed one k-group at a time it was 80 % load latency)
         const int j = t & 63;
         const bool in = j0 + j < n;
-        for (int g = t >> 6; g < 32; g += 4) {
-            double v[4];
+        double v[8][4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = (in && k0 + 4 * g + e < n_rows) ? A[(size_t)(k0 + 4 * g + e) * lda + j0 + j] : 0.0;
+        for (int u = 0; u < 8; ++u) {
+            const int g = (t >> 6) + 4 * u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[u][e] = (in && k0 + 4 * g + e < n_rows) ? A[(size_t)(k0 + 4 * g + e) * lda + j0 + j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int g = (t >> 6) + 4 * u;
             double2* dst = reinterpret_cast<double2*>(sB + g * 256 + j * 4);
-            dst[0] = make_double2(v[0], v[1]);
-            dst[1] = make_double2(v[2], v[3]);
+            dst[0] = make_double2(v[u][0], v[u][1]);
+            dst[1] = make_double2(v[u][2], v[u][3]);
         }
     }
     __syncthreads();
