@@ -10,9 +10,9 @@ The marginal likelihood and the posterior run on this package's fp64 Cholesky (`
 the dense inverse (`CholeskyFactor.inverse`).
 
 One deliberate difference from gpytorch: inside an autograd graph the diagonal shifts (`+ 1e-6 I`, `+ noise I`) are applied
-IN PLACE to the covariance the kernel just produced (an N x N identity and two extra passes per shift otherwise), so
-`output.covariance_matrix` of a training-mode `model(x)` holds the shifted matrix after `mll(output, y)` was evaluated.
-Tensors outside a graph (eval mode, `torch.no_grad()`) are never modified."""
+IN PLACE to the covariance `ExactGPModel.forward` just produced (an N x N identity and two extra passes per shift otherwise),
+so `output.covariance_matrix` of a training-mode `model(x)` holds the shifted matrix after `mll(output, y)` was evaluated.
+Matrices the caller built (a `MultivariateNormal` of their own) and tensors outside a graph are never modified."""
 from __future__ import annotations
 
 import math
@@ -70,10 +70,11 @@ class _AddToDiagonal(torch.autograd.Function):
         return grad, g_shift
 
 
-def _add_to_diagonal(covar, shift):
-    """covar + shift * I; in place when covar is a non-leaf tensor nobody else holds (our kernels' outputs), else a copy."""
+def _add_to_diagonal(covar, shift, owned):
+    """covar + shift * I; in place only when `owned` says the buffer was produced inside this module (the kernel's fresh
+    output inside ExactGPModel.forward) and it is part of an autograd graph; any other tensor is copied first."""
     shift_t = shift if isinstance(shift, torch.Tensor) else torch.tensor([shift], dtype=dtype, device=covar.device)
-    if covar.is_leaf or covar.stride(1) != 1:
+    if not owned or covar.is_leaf or covar.stride(1) != 1:
         covar = covar.clone()
     return _AddToDiagonal.apply(covar, shift_t)
 
@@ -81,9 +82,10 @@ def _add_to_diagonal(covar, shift):
 class MultivariateNormal:
     """The slice of `gpytorch.distributions.MultivariateNormal` the reference's scripts use."""
 
-    def __init__(self, mean, covariance_matrix):
+    def __init__(self, mean, covariance_matrix, owns_covariance=False):
         self.mean = mean
         self.covariance_matrix = covariance_matrix
+        self.owns_covariance = owns_covariance          # the matrix was produced by this module: later shifts may reuse it
 
     loc = property(lambda self: self.mean)
 
@@ -111,7 +113,8 @@ class GaussianLikelihood(torch.nn.Module):
         return torch.nn.functional.softplus(self.raw_noise) + 1e-4
 
     def forward(self, dist: MultivariateNormal) -> MultivariateNormal:
-        return MultivariateNormal(dist.mean, _add_to_diagonal(dist.covariance_matrix, self.noise))
+        owned = getattr(dist, "owns_covariance", False)
+        return MultivariateNormal(dist.mean, _add_to_diagonal(dist.covariance_matrix, self.noise, owned), owns_covariance=owned)
 
 
 class ConstantMean(torch.nn.Module):
@@ -146,8 +149,8 @@ class ExactGPModel(torch.nn.Module):
 
     def forward(self, x):
         mean_x = self.mean_module(x)
-        covar_x = _add_to_diagonal(_dense(self.covar_module(self._points(x))), 1e-6)
-        return MultivariateNormal(mean_x, covar_x)
+        covar_x = _add_to_diagonal(_dense(self.covar_module(self._points(x))), 1e-6, owned=True)
+        return MultivariateNormal(mean_x, covar_x, owns_covariance=True)
 
     def train(self, mode=True):
         self._cache = None
