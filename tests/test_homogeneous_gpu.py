@@ -85,3 +85,38 @@ def test_prior_covariance_matches_kernel_statistically():
     x = space.rand(12)
     with torch.no_grad():
         assert torch.allclose(sampler._cov(x, x), kern(x, x), atol=0.12)
+
+
+@pytest.mark.parametrize("kind,n,m,order,avg", [
+    ("stiefel", 5, 2, 10, 12), ("stiefel", 5, 4, 10, 6), ("stiefel", 5, 3, 20, 10), ("grassmannian", 5, 2, 10, 12),
+    ("oriented_grassmannian", 5, 3, 10, 9), ("grassmannian", 5, 3, 20, 8), ("stiefel", 5, 1, 10, 8), ("stiefel", 5, 3, 26, 6)])
+def test_so5_quotients_against_oracle(kind, n, m, order, avg):
+    """SO(5)/H through every instantiation of `homog5_stair_kernel` (staircase of the first 10 / 20 irreps x subgroup samples
+    of the form blockdiag(I_t, R) with t = 3 [V(5,3), V(5,4)], t = 2 [V(5,2)] or general [Grassmannians, V(5,1)]) and the
+    generic fallback (26 irreps): EigenbasisSumKernel and the per-irrep feature map against the oracle on the same points and
+    the same subgroup samples, ragged sizes."""
+    import lsk_oracle as orc
+    from liestationarykernels_b200 import spaces
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel, RandomPhaseKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(31)
+    oh = orc.Homogeneous(kind, n, m, order=order, average_order=avg)
+    nx, ny, P = 37, 29, 12
+    x, y, phases = oh.rand(nx), oh.rand(ny), oh.rand(P)
+    om = orc.Measure("matern", oh.dim, 0.9, 2.5, 1.3)
+    cls = {"stiefel": spaces.Stiefel, "grassmannian": spaces.Grassmannian, "oriented_grassmannian": spaces.OrientedGrassmannian}[kind]
+    space = cls(n, m, order=order, average_order=avg)
+    space.h_samples = oh.h_samples.cuda()
+    expect_block = {("stiefel", 2): 2, ("stiefel", 3): 3, ("stiefel", 4): 3}.get((kind, m), 0)
+    assert space._identity_block(space.h_samples) == expect_block
+    meas = MaternSpectralMeasure(oh.dim, 0.9, 2.5, 1.3)
+    with torch.no_grad():
+        kern = EigenbasisSumKernel(meas, space).eval()
+        ref = orc.eigensum_unnormalised(oh, om, x, y)
+        got = kern(x.cuda(), y.cuda(), normalize=False).cpu()
+        assert scaled_err(got, ref) < 1e-10
+        rp = RandomPhaseKernel(meas, space, phase_order=P).eval()
+        rp.phases = phases.cuda()
+        emb_ref = orc.random_phase_embedding(oh, om, phases, x, torch.sqrt)
+        emb = rp.make_embedding(x.cuda()).cpu()
+        assert scaled_err(emb, emb_ref) < 1e-10
