@@ -103,3 +103,63 @@ def test_random_phase_kernel_hyperparameter_gradients(case, P):
         k3 = kern(x.cuda(), y.cuda()).evaluate()
     assert scaled_err(k2.detach().cpu(), k3.cpu()) < 1e-13
     assert k2.requires_grad and not k3.requires_grad
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (70, 19), (128, 64), (513, 1000), (2049, 257)])
+def test_panel_matvec_and_column_block_gram(n, k):
+    """lsk_panel_gemv and the column-block Gram (operand pointers advanced by whole k-groups) against dense torch"""
+    from liestationarykernels_b200 import ops
+    torch.manual_seed(n + k)
+    a = torch.randn(n, k, dtype=torch.float64, device="cuda")
+    w = torch.randn(k, dtype=torch.float64, device="cuda")
+    pa = ops.PanelMatrix.from_dense(a)
+    got = ops.panel_matvec(pa, w, 0.75)
+    ref = 0.75 * (a @ w)
+    assert (got - ref).abs().max().item() <= 1e-13 * max(1.0, ref.abs().max().item()) * k ** 0.5
+    assert torch.equal(got, ops.panel_matvec(pa, w, 0.75))                      # deterministic
+    if k >= 8:
+        m = max(n // 2, 1)
+        b = torch.randn(m, k, dtype=torch.float64, device="cuda")
+        pb = ops.PanelMatrix.from_dense(b)
+        g0, g1 = 1, min(pa.kg, 1 + max((k // 4) // 2, 1))
+        blk = ops.gram_columns(pa, pb, g0, g1, 2.0)
+        c0, c1 = 4 * g0, min(4 * g1, k)
+        ref_blk = 2.0 * a[:, c0:c1] @ b[:, c0:c1].T
+        assert (blk - ref_blk).abs().max().item() <= 1e-12 * max(1.0, ref_blk.abs().max().item())
+
+
+@pytest.mark.parametrize("n,k,ld_pad", [(64, 128, 0), (200, 128, 8), (333, 256, 1), (1000, 64, 0), (1111, 128, 6)])
+def test_rank_k_update_epilogue(n, k, ld_pad):
+    """SYRK kind of lsk_pairwise_poly: out += scale * A B^T in place, rectangular and on the triangular tile schedule (tiles
+    that reach the diagonal or lie right of it), ragged sizes, padded / odd leading dimension (scalar-store path)."""
+    import ctypes
+    from liestationarykernels_b200 import _lib, ops
+    lib = _lib.load()
+    torch.manual_seed(n)
+    a = torch.randn(n, k, dtype=torch.float64, device="cuda")
+    b = torch.randn(n - n // 3, k, dtype=torch.float64, device="cuda")
+    pa, pb = ops.PanelMatrix.from_dense(a), ops.PanelMatrix.from_dense(b)
+    ld = n + ld_pad
+    for tri in (0, 1):
+        rows, cols, right = (n, n, pa) if tri else (n, b.shape[0], pb)
+        full = torch.randn(rows, ld, dtype=torch.float64, device="cuda")
+        before = full.clone()
+        ep = _lib.LskEpilogue()
+        ep.kind, ep.nforms, ep.nvars, ep.nterms = _lib.EPI_SYRK, 1, 1, 1
+        ep.group_begin[0], ep.group_end[0] = 0, pa.kg
+        ep.scale, ep.out_layout, ep.reserved = -1.5, _lib.OUT_ROW_MAJOR, 2 * tri
+        rc = lib.lsk_pairwise_poly(_lib.ptr(pa.buf), _lib.ptr(right.buf), rows, cols, pa.kg, ctypes.byref(ep), _lib.ptr(full), ld,
+                                   _lib.stream_ptr())
+        assert rc == 0
+        want = before[:, :cols] - 1.5 * a @ (a if tri else b).T
+        diff = (full[:, :cols] - want).abs()
+        if tri:
+            # entries in tiles that reach the diagonal are updated (128-row x 64-column tiles); below them the matrix is untouched
+            ii = torch.arange(rows, device="cuda")[:, None]
+            jj = torch.arange(cols, device="cuda")[None, :]
+            touched = (jj // 64) >= 2 * (ii // 128)
+            assert diff[touched].max().item() <= 1e-12 * k ** 0.5
+            assert torch.equal(full[:, :cols][~touched], before[:, :cols][~touched])
+        else:
+            assert diff.max().item() <= 1e-12 * k ** 0.5
+        assert torch.equal(full[:, cols:], before[:, cols:])                    # padding columns untouched
