@@ -346,6 +346,15 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 
     int stage = 0, qc = 0;          // ring stage and sequence number of the chunk this warp consumes next
     uint32_t phase = 0;
+    // the cut of every form into chunks does not depend on the tile: count, floor size and remainder come from per-kernel
+    // state (the two integer divisions of chunk_len() sat on the critical path of every chunk of every tile)
+    // (the producer state in shared memory already holds them: pstate[5 + 3 f] floor size, pstate[6 + 3 f] remainder)
+    // tile cursor of the rectangular schedule: advanced by (gridDim / col_panels, gridDim % col_panels) with a carry
+    int cur_r = 0, cur_c = 0, step_r = 0, step_c = 0;
+    if constexpr (!SYM) {
+        cur_r = (int)((long long)blockIdx.x / col_panels); cur_c = (int)((long long)blockIdx.x % col_panels);
+        step_r = (int)((long long)gridDim.x / col_panels); step_c = (int)((long long)gridDim.x % col_panels);
+    }
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
 #ifdef LSK_TRACE
         ++tile_no;
@@ -353,7 +362,12 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
 #endif
         LSK_GSTAMP(0);
         int pr, pc;
-        tile_coords(t, pr, pc);
+        if constexpr (SYM) tile_coords(t, pr, pc);
+        else {
+            pr = cur_r; pc = cur_c;
+            cur_r += step_r; cur_c += step_c;
+            if (cur_c >= col_panels) { cur_c -= col_panels; ++cur_r; }
+        }
         double acc[NF][MT][2][2];
 #pragma unroll
         for (int f = 0; f < NF; ++f)
@@ -389,9 +403,10 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
         //      one pipeline stage each; inside a stage all offsets are immediates ----
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-            const int g_end = p.group_end[f];
-            for (int g = p.group_begin[f], ng; g < g_end; g += ng) {
-                ng = chunk_len(g_end - g);
+            const int cut_cnt = (p.group_end[f] - p.group_begin[f] + KG_PER_STAGE - 1) / KG_PER_STAGE;     // constant divisor: a shift
+            const int cut_base = pstate[5 + 3 * f], cut_rem = pstate[6 + 3 * f];
+            for (int ci = 0; ci < cut_cnt; ++ci) {
+                const int ng = cut_base + (ci < cut_rem ? 1 : 0);
                 produce_ahead();
                 ensure_issued(qc);
                 LSK_GSTAMP(1 + 2 * chunk_no);
