@@ -474,6 +474,7 @@ homog5_stair_kernel(const double* __restrict__ gx, const double* __restrict__ gy
             sh[q] = h[(size_t)(k0 + k) * N_ * N_ + (MTOP + r) * N_ + (MTOP + c)];
         }
         __syncthreads();
+#pragma unroll 2
         for (int k = 0; k < kc; ++k) {
             const double* hk = sh + k * W * W;
             // G[a][MTOP + b] = sum_c M[a][MTOP + c] h[MTOP + b][MTOP + c]
