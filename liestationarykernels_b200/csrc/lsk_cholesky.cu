@@ -361,11 +361,12 @@ bwd_update_kernel(const double* __restrict__ U, long long lda, int k0, int nb, c
 // ------------------------------------------------------------------------------------------------------------
 // row panel of the factor, columns [col0, n), into the panel-major operand layout: P[c][kk] = U[k0 + kk][col0 + c]
 __global__ void __launch_bounds__(256)
-repack_kernel(const double* __restrict__ U, long long lda, long long n, int k0, long long col0, double* __restrict__ P)
+repack_kernel(const double* __restrict__ U, long long lda, long long n, int k0, long long col0, double* __restrict__ P,
+              int kg_stride, int g_off)
 {
     const int t = threadIdx.x, j = t & 63;
     const long long c = col0 + 64ll * blockIdx.x + j;
-    double* Pp = P + (size_t)blockIdx.x * (32 * 256);
+    double* Pp = P + ((size_t)blockIdx.x * kg_stride + g_off) * 256;
     for (int g = t >> 6; g < 32; g += 4) {
         double v[4];
 #pragma unroll
@@ -524,9 +525,12 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
 extern "C" long long lsk_potri_work_doubles(long long n) {
     using namespace lsk::chol;
     if (n < 0) return LSK_ESIZE;
-    return ((n * n + 15) / 16) * 16 + 2 * (((n + 127) / 128) * 128) * NB;
+    return ((n * n + 15) / 16) * 16 + 2 * ((((n + 127) / 128) * 128) + 128) * (2 * NB);
 }
 
+// Two block rows of Y per pair of updates (K = 256, like the factorisation):
+//   Y1 = W_k^T Yb_k;   strip: Yb_{k+1} -= U_k[:, block k+1]^T Y1 (K = 128);   Y2 = W_{k+1}^T Yb_{k+1};
+//   Yb_i -= [U_k; U_{k+1}][:, i]^T [Y1; Y2]  for the rows behind;   out[0:n2, 0:n2] += [Y1; Y2]^T [Y1; Y2]  (triangular schedule)
 extern "C" int lsk_potri_upper(const void* U_, long long n, long long lda, const void* potrf_work, void* work_, void* out_,
                                long long ld_out, void* stream) {
     using namespace lsk;
@@ -538,8 +542,10 @@ extern "C" int lsk_potri_upper(const void* U_, long long n, long long lda, const
     const double* U = static_cast<const double*>(U_);
     const double* W = static_cast<const double*>(potrf_work);
     double* Yb = static_cast<double*>(work_);
+    constexpr int KG2 = 2 * NB / 4;
+    const long long panel_rows = (((n + 127) / 128) * 128) + 128;
     double* PU = Yb + ((n * n + 15) / 16) * 16;          // 128-byte aligned operands (bulk copies)
-    double* PY = PU + (((n + 127) / 128) * 128) * NB;
+    double* PY = PU + panel_rows * (2 * NB);
     double* out = static_cast<double*>(out_);
     cudaError_t e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
     if (e != cudaSuccess) return (int)e;
@@ -550,22 +556,35 @@ extern "C" int lsk_potri_upper(const void* U_, long long n, long long lda, const
     LskEpilogue ep = {};
     ep.kind = LSK_EPI_SYRK; ep.nforms = 1; ep.nvars = 1; ep.nterms = 1;
     ep.out_layout = LSK_OUT_ROW_MAJOR;
-    ep.group_begin[0] = 0; ep.group_end[0] = NB / 4;
+    ep.group_begin[0] = 0;
     const long long nblk = n_blocks(n);
-    for (long long blk = 0; blk < nblk; ++blk) {
+    auto panels = [](long long cols) { return (unsigned)(((cols + 127) / 128) * 2); };
+    for (long long blk = 0; blk < nblk; blk += 2) {
         const long long k0 = blk * NB;
-        const long long nk = (k0 + NB) < n ? (k0 + NB) : n;       // columns of U^{-T} that rows of this block reach
-        const long long m = n - nk;                               // rows behind the block
-        trsm_kernel<<<(unsigned)(((nk + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(Yb, n, n, 0, nk, (int)k0, W + blk * WBLK, PY, NB / 4, 0);
+        const long long n1 = (k0 + NB) < n ? (k0 + NB) : n;       // columns the first block row reaches
+        const bool two = n1 < n;
+        const long long n2 = two ? ((n1 + NB) < n ? (n1 + NB) : n) : n1;
         int rc;
-        if (m > 0) {
-            repack_kernel<<<(unsigned)(((m + 127) / 128) * 2), 256, 0, st>>>(U, lda, n, (int)k0, nk, PU);
-            ep.scale = -1.0; ep.reserved = 0;
-            rc = lsk_pairwise_poly(PU, PY, m, nk, NB / 4, &ep, Yb + nk * n, n, stream);
+        // first block row; its panel is zero-filled up to column n2 so that it can sit next to the second one
+        trsm_kernel<<<panels(n2), TRSM_THREADS, TRSM_SMEM, st>>>(Yb, n, n, 0, n1, (int)k0, W + blk * WBLK, PY, KG2, 0);
+        if (two) {
+            const long long m1 = n - n1;
+            repack_kernel<<<panels(m1), 256, 0, st>>>(U, lda, n, (int)k0, n1, PU, KG2, 0);
+            ep.group_end[0] = NB / 4; ep.scale = -1.0; ep.reserved = 0;
+            rc = lsk_pairwise_poly(PU, PY, n2 - n1, n1, KG2, &ep, Yb + n1 * n, n, stream);             // strip, K = 128
             if (rc != 0) return rc;
+            trsm_kernel<<<panels(n2), TRSM_THREADS, TRSM_SMEM, st>>>(Yb, n, n, 0, n2, (int)n1, W + (blk + 1) * WBLK, PY, KG2, NB / 4);
+            const long long m2 = n - n2;
+            if (m2 > 0) {
+                double* PU2 = PU + 2ll * KG2 * 256;               // operand rows relative to n2 = n1 + 128: two panels further
+                repack_kernel<<<panels(m2), 256, 0, st>>>(U, lda, n, (int)n1, n2, PU2, KG2, NB / 4);
+                ep.group_end[0] = KG2; ep.scale = -1.0; ep.reserved = 0;
+                rc = lsk_pairwise_poly(PU2, PY, m2, n2, KG2, &ep, Yb + n2 * n, n, stream);             // rows behind, K = 256
+                if (rc != 0) return rc;
+            }
         }
-        ep.scale = 1.0; ep.reserved = 2;
-        rc = lsk_pairwise_poly(PY, PY, nk, nk, NB / 4, &ep, out, ld_out, stream);
+        ep.group_end[0] = two ? KG2 : NB / 4; ep.scale = 1.0; ep.reserved = 2;
+        rc = lsk_pairwise_poly(PY, PY, n2, n2, KG2, &ep, out, ld_out, stream);                          // A^{-1} += Y^T Y
         if (rc != 0) return rc;
     }
     mirror_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32)), 256, 0, st>>>(out, ld_out, n);
@@ -608,7 +627,7 @@ extern "C" int lsk_trsm_lower(const void* U_, long long n, long long lda, const 
         const long long m = n - nk;
         trsm_kernel<<<(unsigned)(((nrhs + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(B, ldb, n, 0, nrhs, (int)k0, W + blk * WBLK, PY, NB / 4, 0);
         if (m > 0) {
-            repack_kernel<<<(unsigned)(((m + 127) / 128) * 2), 256, 0, st>>>(U, lda, n, (int)k0, nk, PU);
+            repack_kernel<<<(unsigned)(((m + 127) / 128) * 2), 256, 0, st>>>(U, lda, n, (int)k0, nk, PU, NB / 4, 0);
             const int rc = lsk_pairwise_poly(PU, PY, m, nrhs, NB / 4, &ep, B + nk * ldb, ldb, stream);
             if (rc != 0) return rc;
         }
