@@ -530,6 +530,8 @@ pairwise_kernel(const double* __restrict__ A, const double* __restrict__ B,
                         double x = p.aff[v][0];
 #pragma unroll
                         for (int f = 0; f < NF; ++f) {
+                            // generated epilogues know which forms enter which variable: zero terms cost nothing
+                            if constexpr (GEN > 0) { if (!((LSK_GEN_AFFMASK[GEN] >> (8 * v + f)) & 1ull)) continue; }
                             const double w = ((p.reserved >> (8 + f)) & 1) ? u[f] * u[f] : u[f];
                             x = fma(p.aff[v][1 + f], w, x);
                         }
@@ -682,6 +684,11 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         const unsigned long long h = gen_hash(p);
         for (const GenEntry& g : LSK_GEN_TABLE) {
             if (g.hash != h || g.nsteps != p.nterms || g.nforms != p.nforms || g.nvars != p.nvars) continue;
+            bool map_ok = true;                 // the affine map must vanish wherever the generated code skips a term
+            for (int v = 0; v < p.nvars; ++v)
+                for (int f = 0; f < p.nforms; ++f)
+                    if (!((g.affmask >> (8 * v + f)) & 1ull) && p.aff[v][1 + f] != 0.0) map_ok = false;
+            if (!map_ok) continue;
             switch (g.id) {
 #define LSK_GEN_CASE(ID, NFV, NVV) case ID: return launch<LSK_EPI_HORNER, NFV, NVV, 1, false, ((NFV) >= 3 ? 2 : 4), ID>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st);
                 LSK_GEN_LIST(LSK_GEN_CASE)

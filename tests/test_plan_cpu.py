@@ -76,7 +76,10 @@ def test_generated_epilogues_match_host_plans():
     sys.path.insert(0, os.path.join(root, "tools"))
     import gen_epilogues
     text = open(gen_epilogues.OUT).read()
-    table = {int(m.group(1), 16): int(m.group(2)) for m in re.finditer(r"\{0x([0-9a-f]{16})ull, (\d+), \d+, \d+, \d+\}", text)}
+    table, masks = {}, {}
+    for m in re.finditer(r"\{0x([0-9a-f]{16})ull, (\d+), \d+, \d+, \d+, 0x([0-9a-f]+)ull\}", text):
+        table[int(m.group(1), 16)] = int(m.group(2))
+        masks[int(m.group(1), 16)] = int(m.group(3), 16)
     from liestationarykernels_b200 import classfn
     rng = np.random.default_rng(0)
     for fam, n, order in gen_epilogues.COMBOS:
@@ -85,3 +88,8 @@ def test_generated_epilogues_match_host_plans():
         ops = [int(np.array([ep.coef[2 * t + 1]]).view(np.uint64)[0]) for t in range(ep.nterms)]
         h = gen_epilogues.fnv(ep.nvars, ops)
         assert table.get(h) == ep.nterms, (fam, n, order)
+        # the generated code skips the terms of the affine map outside the recorded mask: they must be zero in the plan
+        for v in range(ep.nvars):
+            for f in range(ep.nforms):
+                if not (masks[h] >> (8 * v + f)) & 1:
+                    assert ep.aff[v][1 + f] == 0.0, (fam, n, order, v, f)
