@@ -262,15 +262,13 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n_rows, long long c
 //   fwd_update_kernel               r_j -= U[k-rows, j]^T z   for the columns j behind the block
 //   bwd_update_kernel               r_i -= U[i, k-cols] z     for the rows i above the block
 // (One fused launch per block made every CTA repeat the 128 x 128 matrix-vector product: 256 CTAs x 128 KB through L2 per
-// step, 26 us per block; split: 11 us.)
+// step, 26 us per block; split: 20 us.  Plain stream-ordered launches: programmatic dependent launches gained 1 % here.)
 __global__ void __launch_bounds__(512)
 block_matvec_kernel(const double* __restrict__ Wg, const double* __restrict__ r, int k0, int nb, int transpose,
                     double* __restrict__ z_out /* [128] scratch */, double* __restrict__ sol /* solution vector */)
 {
     __shared__ double rk[NB];
     const int t = threadIdx.x;
-    pdl_launch_dependents();                         // the next launch of the chain may become resident now ...
-    pdl_wait();                                      // ... and, like this one, waits here for its predecessor to finish
     if (t < NB) rk[t] = t < nb ? r[k0 + t] : 0.0;
     __syncthreads();
     const int row = t >> 2, sub = t & 3;             // four threads per output entry
@@ -301,8 +299,6 @@ fwd_update_kernel(const double* __restrict__ U, long long lda, long long n, int 
 {
     __shared__ double z[NB], part[4][64];
     const int t = threadIdx.x;
-    pdl_launch_dependents();
-    pdl_wait();
     if (t < NB) z[t] = zg[t];
     __syncthreads();
     const int tx = t & 63, ty = t >> 6;
@@ -333,8 +329,6 @@ bwd_update_kernel(const double* __restrict__ U, long long lda, int k0, int nb, c
 {
     __shared__ double z[NB];
     const int t = threadIdx.x;
-    pdl_launch_dependents();
-    pdl_wait();
     if (t < NB) z[t] = zg[t];
     __syncthreads();
     const int sub = t & 3;
@@ -496,8 +490,8 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
             const long long k0 = blk * NB;
             const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
             const long long m = n - k0 - nb;
-            launch_pdl(block_matvec_kernel, dim3(1), dim3(512), 0, st, W + blk * WBLK, (const double*)cur, (int)k0, nb, 0, zbuf, oth);
-            if (m > 0) launch_pdl(fwd_update_kernel, dim3((unsigned)((m + 63) / 64)), dim3(256), 0, st, U, lda, n, (int)k0, nb, (const double*)zbuf, cur);
+            block_matvec_kernel<<<1, 512, 0, st>>>(W + blk * WBLK, cur, (int)k0, nb, 0, zbuf, oth);
+            if (m > 0) fwd_update_kernel<<<(unsigned)((m + 63) / 64), 256, 0, st>>>(U, lda, n, (int)k0, nb, zbuf, cur);
         }
         double* sw = cur; cur = oth; oth = sw;
     }
@@ -505,8 +499,8 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
         for (long long blk = nblk - 1; blk >= 0; --blk) {
             const long long k0 = blk * NB;
             const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
-            launch_pdl(block_matvec_kernel, dim3(1), dim3(512), 0, st, W + blk * WBLK, (const double*)cur, (int)k0, nb, 1, zbuf, oth);
-            if (k0 > 0) launch_pdl(bwd_update_kernel, dim3((unsigned)((k0 + 63) / 64)), dim3(256), 0, st, U, lda, (int)k0, nb, (const double*)zbuf, cur);
+            block_matvec_kernel<<<1, 512, 0, st>>>(W + blk * WBLK, cur, (int)k0, nb, 1, zbuf, oth);
+            if (k0 > 0) bwd_update_kernel<<<(unsigned)((k0 + 63) / 64), 256, 0, st>>>(U, lda, (int)k0, nb, zbuf, cur);
         }
         double* sw = cur; cur = oth; oth = sw;
     }
