@@ -65,3 +65,19 @@ def test_compute_fails_loudly_without_cuda():
     from liestationarykernels_b200.spaces import SO
     with pytest.raises(_lib.LskError):
         SO(3, order=5)
+
+
+def test_error_strings_are_stateless_and_cover_the_codes():
+    """lsk_error_string needs no device: the text of every LSK_E* code and of a CUDA error code"""
+    from liestationarykernels_b200 import _lib
+    lib = _lib.load()
+    assert lib.lsk_error_string(0) == b"ok"
+    assert lib.lsk_error_string(-1) == b"invalid argument"
+    assert lib.lsk_error_string(-2) == b"size out of supported range"
+    assert lib.lsk_error_string(-3) == b"configuration not compiled"
+    assert lib.lsk_error_string(-99) == b"unknown error code"
+    assert lib.lsk_error_string(2)            # cudaErrorMemoryAllocation: some non-empty text from the runtime
+    with pytest.raises(_lib.LskError, match="size out of supported range"):
+        _lib.check(-2, "probe")
+    assert lib.lsk_potrf_work_doubles(0) >= 0 and lib.lsk_potrf_work_doubles(300) > lib.lsk_potrf_work_doubles(0)
+    assert lib.lsk_potri_work_doubles(-1) == -2 and lib.lsk_trsm_work_doubles(128, 5) > 0
