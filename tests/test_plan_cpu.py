@@ -93,3 +93,22 @@ def test_generated_epilogues_match_host_plans():
             for f in range(ep.nforms):
                 if not (masks[h] >> (8 * v + f)) & 1:
                     assert ep.aff[v][1 + f] == 0.0, (fam, n, order, v, f)
+
+
+def test_sphere_dimensions_and_zonal_rows_at_the_pole():
+    """num_harmonics against the closed forms for S^2, S^3, S^4 and every Chebyshev row of the zonal plan at t = 1, where the
+    phase function equals the dimension of its eigenspace (also for the degrees >= 25 that follow the reference's
+    recurrence quirk: they are normalised at t = 1 as well)"""
+    from liestationarykernels_b200.spaces.sphere import _ZonalPlan, num_harmonics
+    for l in range(0, 40):
+        assert num_harmonics(3, l) == 2 * l + 1
+        assert num_harmonics(4, l) == (l + 1) ** 2
+        assert num_harmonics(5, l) == (l + 1) * (l + 2) * (2 * l + 3) // 6
+    for n, order, step in ((2, 30, 1), (3, 28, 1), (4, 16, 2)):
+        degrees = [step * i for i in range(order)]
+        dims = [num_harmonics(n + 1, d) for d in degrees]
+        plan = _ZonalPlan(n, degrees, dims)
+        at_one = plan.M.sum(axis=1)                      # T_k(1) = 1
+        assert np.allclose(at_one, dims, rtol=1e-12, atol=0)
+        ep = plan.epilogue(np.ones(len(degrees)), 1.0)
+        assert ep.nforms == 1 and ep.nvars == 1 and ep.nterms == max(degrees) + 1
