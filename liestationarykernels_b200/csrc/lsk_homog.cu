@@ -565,6 +565,8 @@ extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const
     if (!lifted_x || !lifted_y || !h_samples || !epi || !out) return LSK_EARG;
     if (n_rows < 0 || n_cols < 0 || n_avg < 1) return LSK_ESIZE;
     if (n_rows == 0 || n_cols == 0) return 0;
+    // the pair kernels index rows / columns with int and put 8 rows per CTA on grid.y (<= 65535)
+    if (n_rows > 8ll * 65535 || n_cols > 0x7fffffffll - 32) return LSK_ESIZE;
     const LskEpilogue& p = *epi;
     if (p.nterms < 1 || p.nterms > LSK_MAX_ROWS) return LSK_EARG;
     if (p.out_layout == LSK_OUT_ROW_MAJOR && ld_out < n_cols) return LSK_ESIZE;

@@ -9,10 +9,10 @@ The marginal likelihood and the posterior run on this package's fp64 Cholesky (`
 `EigenbasisSumKernel`'s fused backward (spectral_kernel._WeightedCharacterSum); the gradient of the log-determinant needs
 the dense inverse (`CholeskyFactor.inverse`).
 
-One deliberate difference from gpytorch: inside an autograd graph the diagonal shifts (`+ 1e-6 I`, `+ noise I`) are applied
-IN PLACE to the covariance `ExactGPModel.forward` just produced (an N x N identity and two extra passes per shift otherwise),
-so `output.covariance_matrix` of a training-mode `model(x)` holds the shifted matrix after `mll(output, y)` was evaluated.
-Matrices the caller built (a `MultivariateNormal` of their own) and tensors outside a graph are never modified."""
+Like gpytorch, every call is pure: the diagonal shifts (`+ 1e-6 I`, `+ noise I`) are carried as a pending scalar on the
+`MultivariateNormal` and applied inside `log_prob` to the copy of the covariance the factorisation overwrites anyway (no
+N x N identity, no extra pass, nothing the caller holds is modified; `likelihood(output)` and `mll(output, y)` can be
+evaluated any number of times on the same `output`)."""
 from __future__ import annotations
 
 import math
@@ -30,12 +30,15 @@ def _dense(k):
 
 
 class _GaussianLogProb(torch.autograd.Function):
-    """log N(resid; 0, covar) for a dense positive-definite covar, with gradients
-       d/dcovar = (alpha alpha^T - covar^{-1}) / 2,   d/dresid = -alpha,   alpha = covar^{-1} resid."""
+    """log N(resid; 0, covar + shift I) for a dense covar, with gradients
+       d/dcovar = (alpha alpha^T - S^{-1}) / 2,  d/dshift = tr(d/dcovar),  d/dresid = -alpha,  S = covar + shift I, alpha = S^{-1} resid.
+    The shift is added to the private copy that the factorisation overwrites; `covar` itself is never written."""
 
     @staticmethod
-    def forward(ctx, covar, resid):
-        f = CholeskyFactor(covar, overwrite=False)
+    def forward(ctx, covar, shift, resid):
+        work = covar.detach().clone(memory_format=torch.contiguous_format)
+        work.diagonal().add_(shift.detach().reshape(()))
+        f = CholeskyFactor(work, overwrite=True)
         alpha = f.solve(resid)
         n = resid.shape[0]
         ctx.factor, ctx.alpha = f, alpha
@@ -44,61 +47,63 @@ class _GaussianLogProb(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         f, alpha = ctx.factor, ctx.alpha
-        grad_covar = grad_resid = None
-        if ctx.needs_input_grad[0]:
+        grad_covar = grad_shift = grad_resid = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             gs = float(g)
             grad_covar = f.inverse().addr_(alpha, alpha, beta=-0.5 * gs, alpha=0.5 * gs)     # one pass over the N x N inverse
-        if ctx.needs_input_grad[1]:
+            if ctx.needs_input_grad[1]:
+                grad_shift = torch.diagonal(grad_covar).sum().reshape(1)
+            if not ctx.needs_input_grad[0]:
+                grad_covar = None
+        if ctx.needs_input_grad[2]:
             grad_resid = -g * alpha
-        return grad_covar, grad_resid
-
-
-class _AddToDiagonal(torch.autograd.Function):
-    """covar + shift * I, written into covar itself when this module owns the buffer (the kernel's fresh output): the
-    reference's `K + 1e-6 * eye` and the likelihood's `+ noise * eye` each cost an N x N identity plus two passes over the
-    matrix otherwise.  Gradients: identity for covar, trace for shift."""
-
-    @staticmethod
-    def forward(ctx, covar, shift):
-        ctx.mark_dirty(covar)
-        covar.diagonal().add_(shift.reshape(()) if isinstance(shift, torch.Tensor) else shift)
-        return covar
-
-    @staticmethod
-    def backward(ctx, grad):
-        g_shift = torch.diagonal(grad).sum().reshape(1) if ctx.needs_input_grad[1] else None
-        return grad, g_shift
-
-
-def _add_to_diagonal(covar, shift, owned):
-    """covar + shift * I; in place only when `owned` says the buffer was produced inside this module (the kernel's fresh
-    output inside ExactGPModel.forward) and it is part of an autograd graph; any other tensor is copied first."""
-    shift_t = shift if isinstance(shift, torch.Tensor) else torch.tensor([shift], dtype=dtype, device=covar.device)
-    if not owned or covar.is_leaf or covar.stride(1) != 1:
-        covar = covar.clone()
-    return _AddToDiagonal.apply(covar, shift_t)
+        return grad_covar, grad_shift, grad_resid
 
 
 class MultivariateNormal:
-    """The slice of `gpytorch.distributions.MultivariateNormal` the reference's scripts use."""
+    """The slice of `gpytorch.distributions.MultivariateNormal` the reference's scripts use.  The covariance is
+    `base + diag_shift * I`; the shift stays symbolic (a [1] tensor on the autograd graph of the noise) until someone needs
+    the dense matrix, so adding jitter or noise never touches the N x N buffer."""
 
-    def __init__(self, mean, covariance_matrix, owns_covariance=False):
+    def __init__(self, mean, covariance_matrix, diag_shift=None):
         self.mean = mean
-        self.covariance_matrix = covariance_matrix
-        self.owns_covariance = owns_covariance          # the matrix was produced by this module: later shifts may reuse it
+        self._base = covariance_matrix
+        self._shift = diag_shift
 
     loc = property(lambda self: self.mean)
 
+    def _shift_tensor(self):
+        if self._shift is None:
+            return torch.zeros(1, dtype=dtype, device=self._base.device)
+        return self._shift
+
+    def add_jitter(self, shift):
+        """N(mean, covariance + shift I) sharing this distribution's base matrix (read-only)."""
+        if not isinstance(shift, torch.Tensor):
+            shift = torch.tensor([shift], dtype=dtype, device=self._base.device)
+        total = shift.reshape(1) if self._shift is None else self._shift + shift.reshape(1)
+        return MultivariateNormal(self.mean, self._base, total)
+
+    @property
+    def covariance_matrix(self):
+        """Dense covariance; a fresh tensor whenever a shift is pending (the base buffer is never modified)."""
+        if self._shift is None:
+            return self._base
+        out = self._base.clone()
+        out.diagonal().add_(self._shift.reshape(()))
+        return out
+
     @property
     def variance(self):
-        return torch.diagonal(self.covariance_matrix)
+        d = torch.diagonal(self._base)
+        return d if self._shift is None else d + self._shift.reshape(())
 
     @property
     def stddev(self):
         return self.variance.clamp_min(0).sqrt()
 
     def log_prob(self, value):
-        return _GaussianLogProb.apply(self.covariance_matrix, value - self.mean)
+        return _GaussianLogProb.apply(self._base, self._shift_tensor(), value - self.mean)
 
 
 class GaussianLikelihood(torch.nn.Module):
@@ -113,8 +118,7 @@ class GaussianLikelihood(torch.nn.Module):
         return torch.nn.functional.softplus(self.raw_noise) + 1e-4
 
     def forward(self, dist: MultivariateNormal) -> MultivariateNormal:
-        owned = getattr(dist, "owns_covariance", False)
-        return MultivariateNormal(dist.mean, _add_to_diagonal(dist.covariance_matrix, self.noise, owned), owns_covariance=owned)
+        return dist.add_jitter(self.noise)
 
 
 class ConstantMean(torch.nn.Module):
@@ -149,8 +153,7 @@ class ExactGPModel(torch.nn.Module):
 
     def forward(self, x):
         mean_x = self.mean_module(x)
-        covar_x = _add_to_diagonal(_dense(self.covar_module(self._points(x))), 1e-6, owned=True)
-        return MultivariateNormal(mean_x, covar_x, owns_covariance=True)
+        return MultivariateNormal(mean_x, _dense(self.covar_module(self._points(x)))).add_jitter(1e-6)
 
     def train(self, mode=True):
         self._cache = None

@@ -41,7 +41,12 @@ class LazyGram:
     __matmul__ = matmul
 
     def diag(self):
-        return self.scale * (self.left.to_dense() * self.right.to_dense()).sum(dim=1)
+        """diag(Fx Fy^T) = row-wise dot products, taken on the panel buffers (same layout on both sides, padding is zero)."""
+        if self.left.rows != self.right.rows:
+            raise ValueError("diag() needs a square Gram")
+        lv = self.left.buf[: self.left.row_panels * self.left.kg * 256].view(self.left.row_panels, self.left.kg, 64, 4)
+        rv = self.right.buf[: self.right.row_panels * self.right.kg * 256].view(self.right.row_panels, self.right.kg, 64, 4)
+        return self.scale * (lv * rv).sum(dim=(1, 3)).reshape(-1)[: self.left.rows]
 
     def __getitem__(self, idx):
         return self.evaluate()[idx]
@@ -174,3 +179,12 @@ class DifferentiableFourierGram(LazyGram):
 
     def __getitem__(self, idx):
         return self.evaluate()[idx]
+
+    # the feature maps are built inside the autograd Function; the matrix-free members go through the dense result
+    def matmul(self, rhs):
+        return self.evaluate() @ rhs
+
+    __matmul__ = matmul
+
+    def diag(self):
+        return torch.diagonal(self.evaluate())

@@ -74,20 +74,21 @@ def pairwise_poly(emb_a: torch.Tensor, emb_b: torch.Tensor, n_rows: int, n_cols:
     mirrored, which halves the work of `kernel(x)` and of a Gram `Phi Phi^T`."""
     _lib.require_cuda()
     lib = _lib.load()
-    if symmetric and n_rows == n_cols and n_rows > 256:
-        epilogue.reserved |= 2
-    else:
-        epilogue.reserved &= ~2
     if out is None:
         out = torch.empty((n_rows, n_cols), dtype=F64, device=emb_a.device)
     else:
         if out.dtype != F64 or out.dim() != 2 or out.shape[0] != n_rows or out.shape[1] != n_cols or out.stride(1) != 1:
             raise ValueError("out must be a float64 [n_rows, n_cols] tensor with unit column stride")
-    if n_rows and n_cols:
-        _lib.check(lib.lsk_pairwise_poly(_lib.ptr(emb_a), _lib.ptr(emb_b), n_rows, n_cols, kg_total,
-                                         ctypes.byref(epilogue), _lib.ptr(out), out.stride(0), _lib.stream_ptr()),
-                   "lsk_pairwise_poly")
-        _lib.count_launch()
+    reserved = epilogue.reserved                      # the struct may be a cached one: flag set for this launch only
+    epilogue.reserved = (reserved | 2) if (symmetric and n_rows == n_cols and n_rows > 256) else (reserved & ~2)
+    try:
+        if n_rows and n_cols:
+            _lib.check(lib.lsk_pairwise_poly(_lib.ptr(emb_a), _lib.ptr(emb_b), n_rows, n_cols, kg_total,
+                                             ctypes.byref(epilogue), _lib.ptr(out), out.stride(0), _lib.stream_ptr()),
+                       "lsk_pairwise_poly")
+            _lib.count_launch()
+    finally:
+        epilogue.reserved = reserved
     return out
 
 

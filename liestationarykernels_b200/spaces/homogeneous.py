@@ -51,6 +51,10 @@ class CompactHomogeneousSpace(AbstractManifold):
 
     def __init__(self, g, h, average_order):
         AbstractManifold.__init__(self)
+        if g.n > 5:
+            # lsk_homog_pairs is instantiated for SO(3), SO(4), SO(5) (csrc/lsk_homog.cu); the reference's tables would allow
+            # SO(6..8) quotients as well, at O(n^3 A) work per pair
+            raise ValueError("homogeneous spaces SO(n)/H are built for n <= 5 (got n = %d)" % g.n)
         self.g, self.h = g, h
         self.dim = self.g.dim - self.h.dim
         self.order, self.average_order = self.g.order, average_order

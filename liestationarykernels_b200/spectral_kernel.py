@@ -52,6 +52,8 @@ class _WeightedCharacterSum(torch.autograd.Function):
         ctx.n_params = len(params)
         with torch.no_grad():
             c = kernel._coefficient_vector(normalize, params)
+        if out is not None:
+            ctx.mark_dirty(out)                           # `out` is an input written in place and returned
         return kernel._evaluate(x, y, c.detach().cpu().numpy(), out)
 
     @staticmethod
@@ -83,6 +85,7 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
     def __init__(self, measure, manifold, form="auto"):
         super().__init__(measure, manifold)
         self.form = form
+        self.assume_static = False
         self._ep_cache = {}
         point = manifold.rand()
         self.normalizer = self.forward(point, point, normalize=False)[0, 0]
@@ -153,14 +156,31 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 
 
-    def _epilogue(self, normalize):
-        """Coefficient block for the current hyper-parameters.  Rebuilt (one L-element device->host read plus a few
-        hundred host flops) only when a hyper-parameter tensor or the normaliser changed since the last call."""
+    def _hyper_values(self, normalize):
+        """Current (lengthscale, variance, nu, normaliser) as host floats: one concatenation and ONE device->host read."""
         m = self.measure
-        key = [normalize, self.form]
+        dev, host = [], []
         for t in (m.lengthscale, m.variance, getattr(m, "nu", None), self.normalizer if normalize else None):
-            key.append(None if t is None else (id(t), t._version, t.data_ptr()) if isinstance(t, torch.Tensor) else t)
-        key = tuple(key)
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                dev.append(t.detach().reshape(-1)[:1].to(dtype))
+            elif t is not None:
+                host.append(float(t))
+        vals = torch.cat(dev).tolist() if dev else []
+        return tuple(vals + host)
+
+    def _epilogue(self, normalize):
+        """Coefficient block for the current hyper-parameters.  The cache is keyed on the parameter VALUES, read back on
+        every call (a write through `.data` changes neither `_version` nor the storage pointer, and the reference re-evaluates
+        the measure on every call, so nothing weaker is a drop-in).  A caller that guarantees frozen hyper-parameters can set
+        `kernel.assume_static = True` to skip the read (tensor identity / version keys only) and `invalidate()` by hand."""
+        m = self.measure
+        if self.assume_static:
+            key = [normalize, self.form]
+            for t in (m.lengthscale, m.variance, getattr(m, "nu", None), self.normalizer if normalize else None):
+                key.append(None if t is None else (id(t), t._version, t.data_ptr()) if isinstance(t, torch.Tensor) else t)
+            key = tuple(key)
+        else:
+            key = (normalize, self.form) + self._hyper_values(normalize)
         hit = self._ep_cache.get("key") == key
         if not hit:
             manifold = self.manifold
@@ -168,6 +188,10 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
             scale = float(torch.abs(m.variance[0]).item() / float(self.normalizer)) if normalize else 1.0
             self._ep_cache = {"key": key, "ep": manifold.plan.epilogue(w, scale, form=self.form)}
         return self._ep_cache["ep"]
+
+    def invalidate(self):
+        """Drop the cached coefficient block (only needed with `assume_static = True`)."""
+        self._ep_cache = {}
 
 
 class RandomPhaseKernel(AbstractSpectralKernel):

@@ -448,15 +448,20 @@ def random_phase_embedding(space, measure, phases, x, scale_fn):
     return torch.cat(cols, dim=1)
 
 
-def random_phase_kernel(space, measure, phases, x, y, normalizer=None):
-    """spectral_kernel.py:111-127; returns the dense Gram the lazy tensor would evaluate to."""
-    ex = random_phase_embedding(space, measure, phases, x, torch.sqrt)
-    ey = random_phase_embedding(space, measure, phases, y, torch.sqrt)
+def random_phase_kernel_from_embeddings(measure, ex, ey, normalizer=None):
+    """spectral_kernel.py:119-127 on ready feature maps (sqrt(a)-scaled, `random_phase_embedding(..., torch.sqrt)`)."""
     if normalizer is not None:
         s = torch.sqrt(torch.abs(measure.variance[0]))
         ex = s * ex / torch.sqrt(normalizer)
         ey = s * ey / torch.sqrt(normalizer)
     return ex @ ey.t().clone()
+
+
+def random_phase_kernel(space, measure, phases, x, y, normalizer=None):
+    """spectral_kernel.py:111-127; returns the dense Gram the lazy tensor would evaluate to."""
+    ex = random_phase_embedding(space, measure, phases, x, torch.sqrt)
+    ey = random_phase_embedding(space, measure, phases, y, torch.sqrt)
+    return random_phase_kernel_from_embeddings(measure, ex, ey, normalizer)
 
 
 def random_phase_sample(space, measure, phases, weights, x, normalizer):
@@ -467,6 +472,12 @@ def random_phase_sample(space, measure, phases, weights, x, normalizer):
         return torch.sqrt(var * a)
 
     emb = random_phase_embedding(space, measure, phases, x, scale) / torch.sqrt(normalizer)
+    return torch.einsum("nm,m->n", emb, weights)
+
+
+def random_phase_sample_from_embedding(measure, emb_sqrt_a, weights, normalizer):
+    """prior_approximation.py:85-88 on a ready sqrt(a)-scaled feature map: sqrt(|var| a) = sqrt(|var|) sqrt(a)."""
+    emb = torch.sqrt(torch.abs(measure.variance[0])) * emb_sqrt_a / torch.sqrt(normalizer)
     return torch.einsum("nm,m->n", emb, weights)
 
 

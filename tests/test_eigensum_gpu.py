@@ -193,3 +193,37 @@ def test_headline_size_sub_blocks_against_oracle():
         kc = kern(torch.matmul(g, x[9000:9256]), torch.matmul(g, y[12000:12300]))
         assert torch.allclose(kc, k[9000:9256, 12000:12300], rtol=1e-11, atol=0)
         assert torch.isfinite(k).all()
+
+
+@pytest.mark.parametrize("how", ["data_fill", "data_copy", "no_grad_inplace", "rebind"])
+def test_eval_mode_follows_hyperparameter_writes(how):
+    """The coefficient block is cached between calls; every way of changing a hyper-parameter must invalidate it, including
+    writes through `.data`, which bump neither `_version` nor the storage pointer (the reference re-evaluates the measure
+    on every call, spectral_kernel.py:45-54)."""
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    space = _space("SO", 3, 20)
+    meas = _measure(dict(kind="matern", dim=3, lengthscale=1.0, nu=2.5))
+    kern = EigenbasisSumKernel(meas, space)
+    kern.eval()
+    torch.manual_seed(2)
+    x, y = space.rand(40), space.rand(30)
+    with torch.no_grad():
+        k1 = kern(x, y).clone()
+        if how == "data_fill":
+            meas.lengthscale.data.fill_(0.5)
+        elif how == "data_copy":
+            meas.lengthscale.data.copy_(torch.tensor([0.5], dtype=torch.float64))
+        elif how == "no_grad_inplace":
+            meas.lengthscale.mul_(0.5)
+        else:
+            meas.lengthscale = torch.nn.Parameter(torch.tensor([0.5], dtype=torch.float64, device="cuda"))
+        k2 = kern(x, y).clone()
+        fresh = EigenbasisSumKernel(_measure(dict(kind="matern", dim=3, lengthscale=0.5, nu=2.5)), space)
+        fresh.eval()
+        fresh.normalizer = kern.normalizer                # eval mode keeps the stored normaliser (SURVEY G5)
+        k3 = fresh(x, y)
+        meas.variance.data.fill_(2.5)
+        k4 = kern(x, y)
+    assert not torch.equal(k1, k2)
+    assert torch.equal(k2, k3)
+    assert torch.allclose(k4, 2.5 * k2, rtol=1e-14, atol=0)

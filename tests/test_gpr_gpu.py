@@ -283,3 +283,34 @@ def test_gp_on_the_other_kernel_families(kind):
     assert (pred.mean - want_mean).abs().max().item() < 1e-7 * max(1.0, y.abs().max().item())
     assert (pred.covariance_matrix - want_cov).abs().max().item() < 1e-7 * scale
     assert pred.variance.min().item() > -1e-9 * scale
+
+
+def test_likelihood_and_mll_are_pure_and_idempotent():
+    """`likelihood(output)` / `mll(output, y)` evaluated twice on the same `output` give the same value, and neither changes
+    `output.covariance_matrix` (gpytorch / reference semantics: examples/gpr_model.py:59-66 may log the loss twice)."""
+    from liestationarykernels_b200 import gpr
+    from liestationarykernels_b200.spaces import SO
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(11)
+    space = SO(3, order=10)
+    kern = EigenbasisSumKernel(MaternSpectralMeasure(3, 0.8, 1.5, 1.7), space)
+    n = 150
+    x = space.rand(n)
+    y = torch.randn(n, dtype=torch.float64, device="cuda")
+    lik = gpr.GaussianLikelihood(device="cuda")
+    model = gpr.ExactGPModel(x.reshape(n, -1), y, lik, kern, space, point_shape=(3, 3))
+    model.train()
+    mll = gpr.ExactMarginalLogLikelihood(lik, model)
+    output = model(x.reshape(n, -1))
+    before = output.covariance_matrix.detach().clone()
+    a = mll(output, y)
+    b = mll(output, y)
+    noisy1 = lik(output).covariance_matrix.detach()
+    noisy2 = lik(output).covariance_matrix.detach()
+    assert a.item() == b.item()
+    assert torch.equal(output.covariance_matrix.detach(), before)
+    assert torch.equal(noisy1, noisy2)
+    assert torch.allclose(noisy1.diagonal() - before.diagonal(), lik.noise.detach().expand(n), rtol=0, atol=1e-14)
+    (a + b).backward()                                    # both graphs are intact
+    assert torch.isfinite(kern.measure.lengthscale.grad).all() and torch.isfinite(lik.raw_noise.grad).all()
