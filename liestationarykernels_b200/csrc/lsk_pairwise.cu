@@ -15,6 +15,7 @@
 // Operand layout ("panel-major", produced by lsk_embed.cu): rows are grouped in panels of 64 (zero-padded to a multiple of 128 rows); inside a panel
 // the data is [k-group g][row r][4 doubles], so (a) one pipeline stage of a panel is one contiguous 16 KB
 // block (one bulk copy) and (b) a DMMA A/B fragment (8 rows x 4 k) is one contiguous, conflict-free 256 B read.
+#include <cstdlib>
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
 #include "lsk_generated_epilogues.cuh"
@@ -40,6 +41,10 @@ namespace lsk {
 // lsk_pairwise_so5.cu: LSK_EUNSUPPORTED when the problem is not one of the compiled SO(5) shapes
 int so5_stair_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                      const LskEpilogue& p, int sms, cudaStream_t stream);
+
+// lsk_gram.cu: out = scale * A B^T on the dedicated Gram kernel (row-major output)
+int gram_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_stride, int kg_len, double* out, long long ld_out,
+                double scale, bool symmetric, int sms, cudaStream_t stream);
 
 constexpr int PANEL_STAGE = KG_PER_STAGE * PANEL * 4;            // one panel, one stage: 2048 doubles = 16 KB
 constexpr int B_STAGE = PANEL_STAGE;
@@ -705,8 +710,14 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         return LSK_EUNSUPPORTED;
     }
     case LSK_EPI_LINEAR:
-        if (p.nforms == 1 && p.nvars == 1) LSK_GO_SYM(LSK_EPI_LINEAR, 1, 1, 1);
-        return LSK_EARG;
+        if (p.nforms != 1 || p.nvars != 1) return LSK_EARG;
+        {
+            // row-major Grams run on the dedicated kernel (lsk_gram.cu); LSK_GRAM_TILE=-1 keeps the generic tile kernel (development)
+            static const bool generic_only = [] { const char* s = getenv("LSK_GRAM_TILE"); return s && atoi(s) < 0; }();
+            if (p.out_layout == LSK_OUT_ROW_MAJOR && !generic_only)
+                return gram_launch(a, b, nr, nc, kg_total, p.group_end[0], o, ld_out, p.scale, want_sym, sms, st);
+        }
+        LSK_GO_SYM(LSK_EPI_LINEAR, 1, 1, 1);
     case LSK_EPI_SYRK:
         if (p.nforms != 1 || p.nvars != 1 || p.out_layout != LSK_OUT_ROW_MAJOR) return LSK_EARG;
         LSK_GO_SYM(LSK_EPI_SYRK, 1, 1, 1);

@@ -31,6 +31,41 @@ def phase_shard(num_phases: int, num_irreps: int, world_size: int, rank: int):
     return lo, hi, idx
 
 
+def triangular_chunks(n: int, world_size: int, rank: int, align: int = 128):
+    """Balanced ownership of the upper triangle of an n x n symmetric matrix: the rows are cut into 2 W chunks (boundaries on
+    multiples of `align`), rank r owns chunks r and 2W-1-r.  Chunk c needs only the columns from its own first row on, so the
+    two chunks of a rank together see 2W+1 column chunks on every rank.  Returns [(lo, hi), ...] (empty chunks dropped)."""
+    chunks = 2 * world_size
+    per = -(-n // chunks)
+    per = -(-per // align) * align
+    bounds = [min(i * per, n) for i in range(chunks + 1)]
+    own = (rank, chunks - 1 - rank)
+    return [(bounds[i], bounds[i + 1]) for i in own if bounds[i + 1] > bounds[i]]
+
+
+def sharded_symmetric_gram(phi, scale: float = 1.0, buffers=None):
+    """Upper triangle of scale * Phi Phi^T, row-sharded by `triangular_chunks`, with no collective: every rank holds the whole
+    panel-major feature map `phi` (an ops.PanelMatrix; recomputing it costs 1-2 % of the Gram) and evaluates, for each of its
+    chunks [lo, hi), the diagonal block on the triangular tile schedule (computed once, mirrored inside the block) and the
+    rectangle right of it in general mode.  Returns [(lo, hi, block)], block = float64 [hi-lo, n-lo] holding columns lo..n-1.
+    With one rank this is the single symmetric-mode launch of `ops.gram(phi, phi)`."""
+    from . import ops
+    ws, rk = world()
+    n = phi.rows
+    if ws == 1:
+        out = None if buffers is None else buffers[0]
+        return [(0, n, ops.gram(phi, phi, scale, out=out))]
+    res = []
+    for i, (lo, hi) in enumerate(triangular_chunks(n, ws, rk)):
+        out = torch.empty((hi - lo, n - lo), dtype=torch.float64, device=phi.buf.device) if buffers is None else buffers[i]
+        rows = phi.row_block(lo, hi)
+        ops.gram(rows, rows, scale, out=out[:, : hi - lo])
+        if hi < n:
+            ops.gram(rows, phi.row_block(hi, n), scale, out=out[:, hi - lo:])
+        res.append((lo, hi, out))
+    return res
+
+
 def sharded_covariance(kernel, x, y=None, **kw):
     """Rows [lo, hi) of kernel(x, y) for this rank. Returns (local_block, lo, hi)."""
     ws, rk = world()

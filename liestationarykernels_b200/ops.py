@@ -126,6 +126,17 @@ class PanelMatrix:
             pm.buf = padded.view(pm.row_panels, 64, pm.kg, 4).permute(0, 2, 1, 3).contiguous().view(-1)
         return pm
 
+    def row_block(self, r0: int, r1: int) -> "PanelMatrix":
+        """Rows [r0, r1) as a PanelMatrix sharing this buffer (no copy): a 128-row-aligned block of the panel-major
+        layout is contiguous.  Used by the multi-GPU Gram to address row / column blocks of one feature map."""
+        if r0 % 128 or not (0 <= r0 <= r1 <= self.rows):
+            raise ValueError("row block must start on a multiple of 128 inside the matrix")
+        pm = PanelMatrix.__new__(PanelMatrix)
+        pm.rows, pm.cols, pm.kg = r1 - r0, self.cols, self.kg
+        pm.row_panels = ((pm.rows + 127) // 128) * 2
+        pm.buf = self.buf[(r0 // 64) * self.kg * 256:]
+        return pm
+
     def to_dense(self) -> torch.Tensor:
         v = self.buf[: self.row_panels * self.kg * 256].view(self.row_panels, self.kg, 64, 4).permute(0, 2, 1, 3)
         return v.reshape(self.row_panels * 64, self.kg * 4)[: self.rows, : self.cols].contiguous()

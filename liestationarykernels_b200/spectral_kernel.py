@@ -87,6 +87,7 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         self.form = form
         self.assume_static = False
         self._ep_cache = {}
+        self._pinned = None
         point = manifold.rand()
         self.normalizer = self.forward(point, point, normalize=False)[0, 0]
 
@@ -108,13 +109,28 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         if not isinstance(manifold, CompactLieGroup):
             return manifold._eigensum(self, x, y, normalize, out)
         plan = manifold.plan
-        ep = self._epilogue(normalize)
         same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides
+        cached = self._ep_cache.get("ep") if self._ep_cache.get("flags") == (normalize, self.form) else None
+        pending = None
+        if cached is not None and not self.assume_static:
+            # Optimistic launch: start the stream-ordered read of the hyper-parameters, launch with the cached coefficient
+            # block, and only then wait for the read.  The read completes when the work queued BEFORE this call has finished, so
+            # the host stays one call ahead of the GPU instead of draining it on every call (a blocking read cost 90 us of idle
+            # GPU per 2.4 ms step at C2).  If a parameter did change, the block is rebuilt and the launch repeated into the same
+            # output - stream order makes the second result the final one.
+            pending = self._enqueue_hyper_read(normalize)
+            ep = cached
+        else:
+            ep = self._epilogue(normalize)
         if same:
             ea = eb = ops.embed(plan, x, "a")
         else:
             ea, eb = ops.embed_pair(plan, x, y)                    # one launch for both operands
-        return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
+        res = ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
+        if pending is not None and self._finish_hyper_read(pending) != self._ep_cache["key"]:
+            ep = self._epilogue(normalize)
+            res = ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=res, symmetric=same)
+        return res
 
     # ---- differentiable path ---------------------------------------------------------------------------------
     def _hyper_parameters(self):
@@ -156,8 +172,7 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         return ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
 
 
-    def _hyper_values(self, normalize):
-        """Current (lengthscale, variance, nu, normaliser) as host floats: one concatenation and ONE device->host read."""
+    def _hyper_tensors(self, normalize):
         m = self.measure
         dev, host = [], []
         for t in (m.lengthscale, m.variance, getattr(m, "nu", None), self.normalizer if normalize else None):
@@ -165,8 +180,31 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
                 dev.append(t.detach().reshape(-1)[:1].to(dtype))
             elif t is not None:
                 host.append(float(t))
+        return dev, host
+
+    def _hyper_values(self, normalize):
+        """Current (lengthscale, variance, nu, normaliser) as host floats: one concatenation and ONE device->host read."""
+        dev, host = self._hyper_tensors(normalize)
         vals = torch.cat(dev).tolist() if dev else []
-        return tuple(vals + host)
+        return (normalize, self.form) + tuple(vals + host)
+
+    def _enqueue_hyper_read(self, normalize):
+        """Asynchronous version of `_hyper_values`: copy into pinned memory on the current stream + an event."""
+        dev, host = self._hyper_tensors(normalize)
+        if not dev:
+            return (None, None, 0, host, normalize)
+        if self._pinned is None or self._pinned.numel() < len(dev):
+            self._pinned = torch.empty(8, dtype=dtype).pin_memory()
+        self._pinned[: len(dev)].copy_(torch.cat(dev), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return (self._pinned, ev, len(dev), host, normalize)
+
+    def _finish_hyper_read(self, pending):
+        buf, ev, n, host, normalize = pending
+        if ev is not None:
+            ev.synchronize()
+        return (normalize, self.form) + tuple((buf[:n].tolist() if n else []) + host)
 
     def _epilogue(self, normalize):
         """Coefficient block for the current hyper-parameters.  The cache is keyed on the parameter VALUES, read back on
@@ -180,13 +218,13 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
                 key.append(None if t is None else (id(t), t._version, t.data_ptr()) if isinstance(t, torch.Tensor) else t)
             key = tuple(key)
         else:
-            key = (normalize, self.form) + self._hyper_values(normalize)
+            key = self._hyper_values(normalize)
         hit = self._ep_cache.get("key") == key
         if not hit:
             manifold = self.manifold
             w = spectral_weights(m, manifold) * manifold._dims
             scale = float(torch.abs(m.variance[0]).item() / float(self.normalizer)) if normalize else 1.0
-            self._ep_cache = {"key": key, "ep": manifold.plan.epilogue(w, scale, form=self.form)}
+            self._ep_cache = {"key": key, "flags": (normalize, self.form), "ep": manifold.plan.epilogue(w, scale, form=self.form)}
         return self._ep_cache["ep"]
 
     def invalidate(self):

@@ -68,3 +68,53 @@ def test_shard_bounds_cover_everything():
             assert max(hi - lo for lo, hi in cuts) - min(hi - lo for lo, hi in cuts) <= 1
     seen = torch.cat([phase_shard(10, 4, 3, r)[2] for r in range(3)])
     assert sorted(seen.tolist()) == list(range(40))
+
+
+def test_triangular_chunks_cover_the_rows_and_balance_the_upper_triangle():
+    """`triangular_chunks`: 2W chunks, rank r owns r and 2W-1-r; together they tile [0, n) exactly, boundaries sit on multiples of
+    128 (panel-major row blocks must), and the tile work of the upper triangle is balanced at BASELINE sizes."""
+    from liestationarykernels_b200.distributed import triangular_chunks
+    for n in (32768, 65536, 16384, 5000, 130, 1):
+        for w in (1, 2, 3, 4, 8):
+            per_rank = [triangular_chunks(n, w, r) for r in range(w)]
+            chunks = sorted(c for cs in per_rank for c in cs)
+            assert chunks[0][0] == 0 and chunks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+            assert all(lo % 128 == 0 for lo, _ in chunks)
+            if n >= 16384:
+                work = [sum((hi - lo) * (n - lo) - (hi - lo) ** 2 / 2 for lo, hi in cs) for cs in per_rank]
+                assert max(work) / min(work) < 1.01
+
+
+def _tri_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from liestationarykernels_b200 import distributed as D
+    torch.manual_seed(0)
+    n, k = 700, 24
+    phi = torch.randn(n, k, dtype=torch.float64)
+    full = phi @ phi.T
+    ok = True
+    covered = torch.zeros(n, n, dtype=torch.bool)
+    for lo, hi in D.triangular_chunks(n, world, rank):
+        block = phi[lo:hi] @ phi[lo:].T                    # the per-chunk product `sharded_symmetric_gram` launches
+        ok = ok and torch.allclose(block, full[lo:hi, lo:], rtol=1e-13, atol=1e-13)
+        covered[lo:hi, lo:] = True
+    parts = [None] * world
+    dist.all_gather_object(parts, covered)
+    union = torch.stack(parts).any(dim=0)
+    ret[rank] = (bool(ok), bool(torch.equal(union | union.T, torch.ones(n, n, dtype=torch.bool))), int(sum(p.sum() for p in parts)))
+    dist.destroy_process_group()
+
+
+def test_triangular_sharding_world2_covers_the_upper_triangle_once():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_tri_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert all(ret[r][0] and ret[r][1] for r in range(2))
+    n = 700
+    # every entry on or above the diagonal is owned by exactly one rank (plus the strictly-lower parts of the diagonal blocks)
+    assert ret[0][2] >= n * (n + 1) // 2 and ret[0][2] < n * (n + 1) // 2 + 4 * 256 * 256

@@ -163,3 +163,26 @@ def test_rank_k_update_epilogue(n, k, ld_pad):
         else:
             assert diff.max().item() <= 1e-12 * k ** 0.5
         assert torch.equal(full[:, cols:], before[:, cols:])                    # padding columns untouched
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_symmetric_gram_reassembles_the_upper_triangle(world, monkeypatch):
+    """`distributed.sharded_symmetric_gram` for every rank of an emulated world on one GPU: row blocks of one panel-major feature map
+    addressed in place (`PanelMatrix.row_block`), diagonal blocks on the triangular tile schedule, rectangles in general mode.
+    Each entry of the upper triangle must be bit-identical to the single-GPU symmetric-mode Gram."""
+    from liestationarykernels_b200 import distributed as D, ops
+    torch.manual_seed(world)
+    n, k = 3000, 260
+    a = torch.randn(n, k, dtype=torch.float64, device="cuda")
+    phi = ops.PanelMatrix.from_dense(a)
+    want = ops.gram(phi, phi, 0.5)
+    assert torch.equal(phi.row_block(1280, 2000).to_dense(), a[1280:2000])
+    seen = torch.zeros(n, n, dtype=torch.bool, device="cuda")
+    for rank in range(world):
+        monkeypatch.setattr(D, "world", lambda ws=world, rk=rank: (ws, rk))
+        for lo, hi, block in D.sharded_symmetric_gram(phi, 0.5):
+            assert block.shape == (hi - lo, n - lo)
+            assert torch.equal(block, want[lo:hi, lo:])
+            assert not seen[lo:hi, lo:].any()
+            seen[lo:hi, lo:] = True
+    assert bool((seen | seen.T).all())
