@@ -42,6 +42,10 @@ namespace lsk {
 int so5_stair_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
                      const LskEpilogue& p, int sms, cudaStream_t stream);
 
+// lsk_pairwise_su4.cu: LSK_EUNSUPPORTED unless the problem is the standard SU(4) one of generated tape `gen_id`
+int su4_tile_launch(int gen_id, const double* A, const double* B, int n_rows, int n_cols, int kg_total, double* out, long long ld_out,
+                    const LskEpilogue& p, int sms, cudaStream_t stream);
+
 // lsk_gram.cu: out = scale * A B^T on the dedicated Gram kernel (row-major output)
 int gram_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_stride, int kg_len, double* out, long long ld_out,
                 double scale, bool symmetric, int sms, cudaStream_t stream);
@@ -694,6 +698,14 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
                 for (int f = 0; f < p.nforms; ++f)
                     if (!((g.affmask >> (8 * v + f)) & 1ull) && p.aff[v][1 + f] != 0.0) map_ok = false;
             if (!map_ok) continue;
+            {
+                // SU(4) has a dedicated kernel (lsk_pairwise_su4.cu); LSK_SU4_GENERIC=1 keeps the generic one (development)
+                static const bool generic_only = [] { const char* s = getenv("LSK_SU4_GENERIC"); return s && atoi(s) > 0; }();
+                if (!generic_only) {
+                    const int rc = su4_tile_launch(g.id, a, b, nr, nc, kg_total, o, ld_out, p, sms, st);
+                    if (rc != LSK_EUNSUPPORTED) return rc;
+                }
+            }
             switch (g.id) {
 #define LSK_GEN_CASE(ID, NFV, NVV) case ID: return launch<LSK_EPI_HORNER, NFV, NVV, 1, false, ((NFV) >= 3 ? 2 : 4), ID>(a, b, nr, nc, kg_total, o, ld_out, p, sms, st);
                 LSK_GEN_LIST(LSK_GEN_CASE)
