@@ -68,6 +68,7 @@ typedef struct LskEpilogue {
     int32_t reserved;                    /* bit 0 (lsk_homog_pairs): pair (y_j, x_i) instead of (x_i, y_j);
                                             bits 4-7 (lsk_homog_pairs, n = 5): t in {0, 2, 3}: the caller vouches that every
                                             subgroup sample is blockdiag(I_t, R) (Stiefel: H = SO(n - m), stiefel.py:25-36);
+                                            11: t = 3 and every R is a plane rotation [[c, s], [-s, c]];
                                             bit 1 (lsk_pairwise_poly): symmetric problem (A, B describe the same points, square
                                             row-major output): only the upper triangle of tiles is computed and mirrored;
                                             bits 8+f (lsk_pairwise_poly): form f enters the affine map squared */
@@ -130,6 +131,16 @@ int lsk_lift_frames(const void* x, long long num, int n, int m, void* out, void*
  * FEAT_SPARSE (n = 4: variables s_1, s_2, z;  n = 5: s_1, s_2) with one row per output (irrep, or a single collapsed polynomial). */
 int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const void* h_samples, long long n_rows, long long n_cols,
                     int n, int n_avg, const LskEpilogue* epi, void* out, long long ld_out, void* stream);
+
+/* Fused prior sample on SO(5)/SO(2) (Stiefel V(5,3), V(5,4)):
+ *   out[i] = sum_l sum_j weights[l * P + j] * Phi[i, l * P + j],   Phi = the per-irrep feature map lsk_homog_pairs would write
+ * for the same arguments (epi: LSK_EPI_FEAT_SPARSE rows, feat_stride = P = n_phases; bits 4-7 of `reserved` must be 11: the caller
+ * vouches that every subgroup sample is blockdiag(I_3, [[c, s], [-s, c]])).  Replaces make_embedding + einsum('nm,m->n') of
+ * RandomPhaseApproximation.forward (reference prior_approximation.py:70-88) without materialising Phi.  lifted_x: [n_rows, 5, 5],
+ * lifted_phases: [n_phases, 5, 5] (both from lsk_lift_frames), h_samples: [n_avg, 5, 5], weights: [nterms * feat_stride], out:
+ * [n_rows]; returns LSK_EUNSUPPORTED (-3) for any other problem shape. */
+int lsk_homog_sample(const void* lifted_x, const void* lifted_phases, const void* h_samples, long long n_rows, long long n_phases,
+                     int n, int n_avg, const LskEpilogue* epi, const void* weights, void* out, void* stream);
 
 /* Spherical-function features on hyperbolic space (ball model):
  *   F[i,k] = scale * coef[k] * ((1-|x_i|^2)/|x_i - shift_k|^2)^(-i lmd_k + (n-1)/2)

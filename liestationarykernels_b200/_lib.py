@@ -66,6 +66,9 @@ _PROTOTYPES = {
     "lsk_homog_pairs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong,
                                        ctypes.c_int, ctypes.c_int, ctypes.POINTER(LskEpilogue), ctypes.c_void_p,
                                        ctypes.c_longlong, ctypes.c_void_p]),
+    "lsk_homog_sample": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong,
+                                        ctypes.c_int, ctypes.c_int, ctypes.POINTER(LskEpilogue), ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
     "lsk_hyp_features": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),

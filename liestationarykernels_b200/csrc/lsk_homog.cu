@@ -545,6 +545,196 @@ homog5_stair_kernel(const double* __restrict__ gx, const double* __restrict__ gy
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// SO(5)/SO(2) with rotation samples (BASELINE config C4: V(5,3), H = SO(2); also V(5,4), whose samples are the identity):
+//   h_k = blockdiag(I_3, R_k),  R_k = [[c, s], [-s, c]]   (stiefel.py:25-36 with so.py:62-70)
+// For such samples the invariants of g = M h_k^T are TRIGONOMETRIC POLYNOMIALS of the sample angle with per-pair constants
+// (M = [[T, U], [V, W]] with T 3x3, W = [[p, q], [r, t]] 2x2, Q = V U):
+//   tr g   = tr T + (p + t) c + (q - r) s
+//   tr g^2 = tr T^2 + (u + v)/2 + 2 (Q00 + Q11) c + 2 (Q01 - Q10) s + (u - v)/2 cos 2phi + (w/2) sin 2phi,
+//            u = p^2 + t^2 + 2 q r,  v = q^2 + r^2 - 2 p t,  w = 2 (p q - r t + q t - p r)
+// so a sample costs 6 multiply-adds for the invariants (the general kernel above: 42) + the staircase monomials; the 5 x 5
+// matrix M is dead once the eight constants exist, which takes the kernel from 126 registers to ~70.  The per-irrep coefficients are
+// applied to the averaged monomials through a DENSE [irrep][monomial] table (built by the host from the sparse list): every
+// index is a compile-time constant, nothing lives in local memory.
+//   MODE 0: per-irrep features, CTA = 64 rows x 4 columns -> every store instruction of a warp writes 8 rows x 32 B of one
+//           k-group of the panel-major map (256 contiguous bytes);
+//   MODE 1: fused prior sample f[i] = sum_l sum_j w[l P + j] Phi[i, l P + j] (prior_approximation.py:85-88): CTA = 8 rows x 32
+//           phase lanes looping over all phases, fixed-order shuffle reduction - the 5.4 GB feature map of C4 is never written.
+// ------------------------------------------------------------------------------------------------------------
+template <unsigned long long SHAPE>
+struct RotPair {
+    using SH = StairShape<SHAPE>;
+    static constexpr int ROWS = SH::rows(), TOTAL = SH::total(), AMAX = SH::amax();
+
+    // eight per-pair constants of the two trigonometric polynomials
+    struct Consts { double t1_0, t1_c, t1_s, t2_0, t2_c, t2_s, t2_c2, t2_s2; };
+
+    __device__ static __forceinline__ Consts pair_constants(const double* __restrict__ gi, const double* __restrict__ gj, bool swap) {
+        // M = lift_i^T lift_j (swap: lift_j^T lift_i), accumulated row pair by row pair: 25 accumulators + 10 operands live
+        double M[5][5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int b = 0; b < 5; ++b) M[a][b] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            double xr[5], yr[5];
+#pragma unroll
+            for (int a = 0; a < 5; ++a) { xr[a] = gi[c * 5 + a]; yr[a] = gj[c * 5 + a]; }
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+                for (int b = 0; b < 5; ++b) M[a][b] = swap ? fma(yr[a], xr[b], M[a][b]) : fma(xr[a], yr[b], M[a][b]);
+        }
+        Consts k;
+        double trT = 0.0, trT2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            trT += M[a][a];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) trT2 = fma(M[a][b], M[b][a], trT2);
+        }
+        const double p = M[3][3], q = M[3][4], r = M[4][3], t = M[4][4];
+        double Q[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) s = fma(M[3 + a][c], M[c][3 + b], s);
+                Q[a][b] = s;
+            }
+        const double u = fma(p, p, fma(t, t, 2.0 * q * r)), v = fma(q, q, fma(r, r, -2.0 * p * t));
+        const double w = 2.0 * (fma(p, q, -r * t) + fma(q, t, -p * r));
+        k.t1_0 = trT; k.t1_c = p + t; k.t1_s = q - r;
+        k.t2_0 = trT2 + 0.5 * (u + v);
+        k.t2_c = 2.0 * (Q[0][0] + Q[1][1]); k.t2_s = 2.0 * (Q[0][1] - Q[1][0]);
+        k.t2_c2 = 0.5 * (u - v); k.t2_s2 = 0.5 * w;
+        return k;
+    }
+
+    // S[m] += monomials of (v0, v1) for one sample (c, s, cos 2phi, sin 2phi)
+    __device__ static __forceinline__ void add_sample(const Consts& k, const double4 cs, const double (&aff)[2][3], double (&S)[TOTAL]) {
+        const double t1 = fma(k.t1_s, cs.y, fma(k.t1_c, cs.x, k.t1_0));
+        const double t2 = fma(k.t2_s2, cs.w, fma(k.t2_c2, cs.z, fma(k.t2_s, cs.y, fma(k.t2_c, cs.x, k.t2_0))));
+        const double e2 = 0.5 * fma(t1, t1, -t2);
+        const double v0 = fma(aff[0][2], e2, fma(aff[0][1], t1, aff[0][0]));
+        const double v1 = fma(aff[1][2], e2, fma(aff[1][1], t1, aff[1][0]));
+        double pa[AMAX + 1];
+        pa[0] = 1.0;
+#pragma unroll
+        for (int a = 1; a <= AMAX; ++a) pa[a] = pa[a - 1] * v0;
+        double pb = 1.0;
+#pragma unroll
+        for (int b = 0; b < ROWS; ++b) {
+#pragma unroll
+            for (int a = 0; a < SH::len(b); ++a) S[SH::offset(b) + a] = fma(pa[a], pb, S[SH::offset(b) + a]);
+            if (b + 1 < ROWS) pb *= v1;
+        }
+    }
+};
+
+constexpr int ROT_CHUNK = 128;          // subgroup samples staged per pass (4 doubles each)
+
+template <unsigned long long SHAPE, int MODE>
+__global__ void __launch_bounds__(256, 3)
+homog5_rot_kernel(const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ h,
+                  int n_rows, int n_cols, int n_avg, double* __restrict__ out, long long ld_out,
+                  const double* __restrict__ weights, const __grid_constant__ LskEpilogue p)
+{
+    using RP = RotPair<SHAPE>;
+    constexpr int TOTAL = RP::TOTAL;
+    __shared__ __align__(32) double4 sh[ROT_CHUNK];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    // MODE 0: blockDim = (4, 64): x = column lane, y = row inside the 64-row panel.  MODE 1: blockDim = (32, 8).
+    const int i = MODE == 0 ? blockIdx.y * 64 + threadIdx.y : blockIdx.x * 8 + threadIdx.y;
+    const bool swap = (p.reserved & 1) != 0;
+    double aff[2][3];
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) aff[v][c] = p.aff[v][c];
+    const double inv_avg = p.scale / (double)n_avg;
+    const int j_begin = MODE == 0 ? blockIdx.x * 4 + threadIdx.x : threadIdx.x;
+    const int j_step = MODE == 0 ? n_cols : 32;             // MODE 0: a single column per thread
+    double fsum = 0.0;
+    for (int j0 = j_begin; j0 < (MODE == 0 ? j_begin + 1 : ((n_cols + 31) / 32) * 32); j0 += j_step) {
+        const int j = j0;
+        const bool active = (i < n_rows) && (j < n_cols);
+        typename RP::Consts k = {};
+        if (active) k = RP::pair_constants(gx + (size_t)i * 25, gy + (size_t)j * 25, swap);
+        double S[TOTAL];
+#pragma unroll
+        for (int m = 0; m < TOTAL; ++m) S[m] = 0.0;
+        for (int k0 = 0; k0 < n_avg; k0 += ROT_CHUNK) {
+            const int kc = min(ROT_CHUNK, n_avg - k0);
+            if (MODE == 0 || n_avg > ROT_CHUNK || j0 == j_begin) {      // MODE 1 with few samples: staged once per CTA
+                __syncthreads();
+                for (int q = tid; q < kc; q += 256) {
+                    const double c = h[(size_t)(k0 + q) * 25 + 18], s = h[(size_t)(k0 + q) * 25 + 19];   // R[0][0], R[0][1]
+                    sh[q] = make_double4(c, s, fma(c, c, -s * s), 2.0 * c * s);
+                }
+                __syncthreads();
+            }
+#pragma unroll 2
+            for (int q = 0; q < kc; ++q) RP::add_sample(k, sh[q], aff, S);
+        }
+        // dense coefficient table: irrep l, monomial m -> coef[l * TOTAL + m]
+        if (MODE == 0) {
+            if (!active) return;
+            for (int l = 0; l < p.nterms; ++l) {
+                double v = 0.0;
+#pragma unroll
+                for (int m = 0; m < TOTAL; ++m) v = fma(p.coef[l * TOTAL + m], S[m], v);
+                v *= inv_avg;
+                const long long c = (long long)l * p.feat_stride + j;
+                double* dst = (p.out_layout == LSK_OUT_PANEL_MAJOR)
+                    ? out + (((size_t)(i >> 6) * p.out_kg + (size_t)(c >> 2)) * PANEL + (i & 63)) * 4 + (c & 3)
+                    : out + (size_t)i * ld_out + c;
+                *dst = v;
+            }
+        } else if (active) {
+            for (int l = 0; l < p.nterms; ++l) {
+                double v = 0.0;
+#pragma unroll
+                for (int m = 0; m < TOTAL; ++m) v = fma(p.coef[l * TOTAL + m], S[m], v);
+                fsum = fma(v * inv_avg, weights[(size_t)l * p.feat_stride + j], fsum);
+            }
+        }
+    }
+    if (MODE == 1) {
+        // fixed-order reduction over the 32 phase lanes of the row
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+        if (threadIdx.x == 0 && i < n_rows) out[i] = fsum;
+    }
+}
+
+// sparse per-irrep monomial lists -> dense [irrep][monomial of the staircase SHAPE]; false if a term falls outside the staircase
+template <unsigned long long SHAPE>
+static bool densify_rows(const LskEpilogue& p, LskEpilogue& q) {
+    using SH = StairShape<SHAPE>;
+    constexpr int TOTAL = SH::total();
+    if (p.nterms * TOTAL > LSK_MAX_COEF) return false;
+    q = p;
+    for (int t = 0; t < LSK_MAX_COEF; ++t) q.coef[t] = 0.0;
+    int pos = 0;
+    for (int l = 0; l < p.nterms; ++l) {
+        for (int t = 0; t < p.row_len[l]; ++t) {
+            unsigned long long e;
+            memcpy(&e, &p.coef[2 * (pos + t) + 1], 8);
+            const int ea = (int)(e & 0xffu), eb = (int)((e >> 8) & 0xffu);
+            if (eb >= SH::rows() || ea >= SH::len(eb)) return false;
+            q.coef[l * TOTAL + SH::offset(eb) + ea] += p.coef[2 * (pos + t)];
+        }
+        pos += p.row_len[l];
+    }
+    return true;
+}
+
 }  // namespace lsk
 
 extern "C" int lsk_lift_frames(const void* x, long long num, int n, int m, void* out, void* bad_count, void* stream) {
@@ -615,8 +805,24 @@ extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const
             for (int b = 0; b < 16; ++b) if (rows[b] > (int)((shape >> (4 * b)) & 15ull)) return false;
             return true;
         };
-        const int mtop = (p.reserved >> 4) & 15;         // the caller vouches: samples are blockdiag(I_mtop, R)
+        int mtop = (p.reserved >> 4) & 15;               // the caller vouches: samples are blockdiag(I_mtop, R)
         constexpr unsigned long long SH10 = 0x235ull, SH20 = 0x13457ull;
+        if (mtop == 11) {
+            // t = 3 and every R is a plane rotation [[c, s], [-s, c]]: trigonometric-polynomial kernel
+            LskEpilogue q;
+            dim3 rblock(4, 64), rgrid((unsigned)((n_cols + 3) / 4), (unsigned)((n_rows + 63) / 64));
+            if (rgrid.y <= 65535u) {
+                if (covered(SH10) && densify_rows<SH10>(p, q)) {
+                    homog5_rot_kernel<SH10, 0><<<rgrid, rblock, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, nullptr, q);
+                    return (int)cudaGetLastError();
+                }
+                if (covered(SH20) && densify_rows<SH20>(p, q)) {
+                    homog5_rot_kernel<SH20, 0><<<rgrid, rblock, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, nullptr, q);
+                    return (int)cudaGetLastError();
+                }
+            }
+            mtop = 3;                                    // other shapes: the block-structured kernel below
+        }
 #define LSK_H5(SHAPE, MT) homog5_stair_kernel<SHAPE, MT><<<grid, block, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, p)
         if (mtop > 4 || mtop == 1) return LSK_EARG;
         if (covered(SH10)) {
@@ -631,5 +837,43 @@ extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const
     } else {
         return LSK_EUNSUPPORTED;
     }
+    return (int)cudaGetLastError();
+}
+
+
+// Fused prior sample on SO(5)/SO(2) (V(5,3) / V(5,4) with rotation samples):  out[i] = sum_l sum_j w[l * P + j] * Phi[i, l * P + j]
+// with Phi the per-irrep feature map lsk_homog_pairs would write (same epilogue struct, FEAT_SPARSE rows, feat_stride = P).
+// Replaces make_embedding + einsum('nm,m->n') of prior_approximation.py:70-88; the feature map is never materialised.
+// LSK_EUNSUPPORTED when the problem is not of that form (the caller then writes the map and reduces it with lsk_panel_gemv).
+extern "C" int lsk_homog_sample(const void* lifted_x, const void* lifted_phases, const void* h_samples, long long n_rows,
+                                long long n_phases, int n, int n_avg, const LskEpilogue* epi, const void* weights, void* out,
+                                void* stream) {
+    using namespace lsk;
+    if (!lifted_x || !lifted_phases || !h_samples || !epi || !weights || !out) return LSK_EARG;
+    if (n_rows < 0 || n_phases < 0 || n_avg < 1) return LSK_ESIZE;
+    if (n_rows > 0x7fffffffll - 64 || n_phases > 0x7fffffffll - 64) return LSK_ESIZE;
+    const LskEpilogue& p = *epi;
+    if (n != 5 || p.kind != LSK_EPI_FEAT_SPARSE || ((p.reserved >> 4) & 15) != 11) return LSK_EUNSUPPORTED;
+    if (p.nterms < 1 || p.nterms > LSK_MAX_ROWS || p.feat_stride < n_phases) return LSK_EARG;
+    int tot = 0;
+    for (int l = 0; l < p.nterms; ++l) { if (p.row_len[l] < 1) return LSK_EARG; tot += p.row_len[l]; }
+    if (2 * tot > LSK_MAX_COEF) return LSK_EARG;
+    if (n_rows == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n_phases == 0) return (int)cudaMemsetAsync(out, 0, (size_t)n_rows * sizeof(double), st);
+    constexpr unsigned long long SH10 = 0x235ull, SH20 = 0x13457ull;
+    LskEpilogue q;
+    dim3 block(32, 8), grid((unsigned)((n_rows + 7) / 8));
+    const double* gx = static_cast<const double*>(lifted_x);
+    const double* gp = static_cast<const double*>(lifted_phases);
+    const double* hh = static_cast<const double*>(h_samples);
+    const double* w = static_cast<const double*>(weights);
+    double* o = static_cast<double*>(out);
+    if (densify_rows<SH10>(p, q))
+        homog5_rot_kernel<SH10, 1><<<grid, block, 0, st>>>(gx, gp, hh, (int)n_rows, (int)n_phases, n_avg, o, 0, w, q);
+    else if (densify_rows<SH20>(p, q))
+        homog5_rot_kernel<SH20, 1><<<grid, block, 0, st>>>(gx, gp, hh, (int)n_rows, (int)n_phases, n_avg, o, 0, w, q);
+    else
+        return LSK_EUNSUPPORTED;
     return (int)cudaGetLastError();
 }

@@ -46,7 +46,10 @@ class RandomPhaseApproximation(torch.nn.Module):
         return self.kernel.manifold._phase_features(x, self.phases, self._row_scales(), panel=False)
 
     def forward(self, x):
-        feats = self.kernel.manifold._phase_features(x, self.phases, self._row_scales(), panel=True)
+        m = self.kernel.manifold
+        if hasattr(m, "_phase_sample"):        # fused: the [N, L * P] feature map is not written where the kernel can reduce it
+            return m._phase_sample(x, self.phases, self._row_scales(), self.weights)
+        feats = m._phase_features(x, self.phases, self._row_scales(), panel=True)
         return ops.panel_matvec(feats, self.weights)
 
     def _cov(self, x, y):

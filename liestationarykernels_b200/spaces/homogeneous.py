@@ -122,9 +122,10 @@ class CompactHomogeneousSpace(AbstractManifold):
         _lib.count_launch()
 
     def _identity_block(self, h):
-        """Largest t in {3, 2} such that every subgroup sample is blockdiag(I_t, R) — true for Stiefel manifolds, whose
-        H = SO(n - m) acts on the last n - m columns (stiefel.py:25-36) — else 0.  lsk_homog_pairs then forms only the
-        columns of lift(x)^T lift(y) h^T that depend on the sample.  Checked on the tensor itself (h_samples is a plain
+        """Structure code of the subgroup samples for lsk_homog_pairs (bits 4-7 of `reserved`): the largest t in {3, 2} such that
+        every sample is blockdiag(I_t, R) - true for Stiefel manifolds, whose H = SO(n - m) acts on the last n - m columns
+        (stiefel.py:25-36) - else 0; 11 when t = 3 and every R is a plane rotation [[c, s], [-s, c]] (V(5,3): H = SO(2), so.py:62-70;
+        V(5,4): R = I), which selects the trigonometric-polynomial kernel.  Checked on the tensor itself (h_samples is a plain
         attribute that callers may replace), once per tensor version."""
         key = (h.data_ptr(), h._version, tuple(h.shape))
         if getattr(self, "_hblock_key", None) != key:
@@ -137,6 +138,12 @@ class CompactHomogeneousSpace(AbstractManifold):
                     if ok:
                         t_found = t
                         break
+                if t_found == 3:
+                    c, s = h[:, 3, 3], h[:, 3, 4]
+                    rot = torch.equal(h[:, 4, 4], c) and torch.equal(h[:, 4, 3], -s) and \
+                        bool((torch.abs(c * c + s * s - 1.0) < 1e-14).all())
+                    if rot:
+                        t_found = 11
             self._hblock_key, self._hblock = key, t_found
         return self._hblock
 
@@ -164,6 +171,32 @@ class CompactHomogeneousSpace(AbstractManifold):
             if N and P:
                 self._pairs(gx, gp, ep, N, P, base, ld)
         return target
+
+    def _phase_sample(self, x, phases, row_scales, weights):
+        """f[n] = sum_l sum_p weights[l * P + p] * Phi[n, l * P + p] with Phi = `_phase_features(x, phases, row_scales)`: the
+        prior sample of RandomPhaseApproximation (prior_approximation.py:85-88).  On SO(5)/SO(2) the feature kernel reduces over
+        the phases itself (`lsk_homog_sample`: the [N, L * P] map is never written); otherwise the map is written panel-major and
+        read once by `lsk_panel_gemv`."""
+        h = self.h_samples.to(dtype).contiguous()
+        N, P = x.shape[0], phases.shape[0]
+        if self.n == 5 and self._identity_block(h) == 11 and N and P:
+            lib = _lib.load()
+            scales = np.asarray(row_scales, dtype=np.float64) * self._dims
+            batches = list(self.plan.feature_epilogues(scales, P, monomial_list=True))
+            if len(batches) == 1 and batches[0][1] == 0:
+                ep = batches[0][0]
+                ep.reserved = 1 | (11 << 4)                  # pair (phase, point); rotation samples
+                gx, gp = self.M_to_G(x), self.M_to_G(phases)
+                w = weights.to(dtype).contiguous()
+                out = torch.empty(N, dtype=dtype, device=x.device)
+                rc = lib.lsk_homog_sample(_lib.ptr(gx), _lib.ptr(gp), _lib.ptr(h), N, P, self.n, h.shape[0], ctypes.byref(ep),
+                                          _lib.ptr(w), _lib.ptr(out), _lib.stream_ptr())
+                if rc == 0:
+                    _lib.count_launch()
+                    return out
+                if rc != -3:                                  # LSK_EUNSUPPORTED falls through to the two-pass path
+                    _lib.check(rc, "lsk_homog_sample")
+        return ops.panel_matvec(self._phase_features(x, phases, row_scales, panel=True), weights)
 
     def _eigensum(self, kernel, x, y, normalize, out=None):
         """EigenbasisSumKernel on M (spectral_kernel.py:37-54 with space.py:131-135, 273-275)."""

@@ -92,7 +92,7 @@ def test_prior_covariance_matches_kernel_statistically():
     ("oriented_grassmannian", 5, 3, 10, 9), ("grassmannian", 5, 3, 20, 8), ("stiefel", 5, 1, 10, 8), ("stiefel", 5, 3, 26, 6)])
 def test_so5_quotients_against_oracle(kind, n, m, order, avg):
     """SO(5)/H through every instantiation of `homog5_stair_kernel` (staircase of the first 10 / 20 irreps x subgroup samples
-    of the form blockdiag(I_t, R) with t = 3 [V(5,3), V(5,4)], t = 2 [V(5,2)] or general [Grassmannians, V(5,1)]) and the
+    of the form blockdiag(I_3, rotation) [V(5,3), V(5,4): `homog5_rot_kernel`], blockdiag(I_2, R) [V(5,2)] or general [Grassmannians, V(5,1)]) and the
     generic fallback (26 irreps): EigenbasisSumKernel and the per-irrep feature map against the oracle on the same points and
     the same subgroup samples, ragged sizes."""
     import lsk_oracle as orc
@@ -107,7 +107,8 @@ def test_so5_quotients_against_oracle(kind, n, m, order, avg):
     cls = {"stiefel": spaces.Stiefel, "grassmannian": spaces.Grassmannian, "oriented_grassmannian": spaces.OrientedGrassmannian}[kind]
     space = cls(n, m, order=order, average_order=avg)
     space.h_samples = oh.h_samples.cuda()
-    expect_block = {("stiefel", 2): 2, ("stiefel", 3): 3, ("stiefel", 4): 3}.get((kind, m), 0)
+    # structure code of the subgroup samples: blockdiag(I_2, R) -> 2; blockdiag(I_3, plane rotation) -> 11 (V(5,3), V(5,4))
+    expect_block = {("stiefel", 2): 2, ("stiefel", 3): 11, ("stiefel", 4): 11}.get((kind, m), 0)
     assert space._identity_block(space.h_samples) == expect_block
     meas = MaternSpectralMeasure(oh.dim, 0.9, 2.5, 1.3)
     with torch.no_grad():
@@ -120,3 +121,35 @@ def test_so5_quotients_against_oracle(kind, n, m, order, avg):
         emb_ref = orc.random_phase_embedding(oh, om, phases, x, torch.sqrt)
         emb = rp.make_embedding(x.cuda()).cpu()
         assert scaled_err(emb, emb_ref) < 1e-10
+
+
+@pytest.mark.parametrize("order,avg,P,N", [(10, 30, 64, 100), (20, 7, 36, 77), (10, 200, 8, 9)])
+def test_fused_stiefel_sampler_equals_feature_map_times_weights(order, avg, P, N):
+    """`lsk_homog_sample` (V(5,3): the feature kernel reduces over the phases itself) against the two-pass path (feature map written
+    panel-major, then `lsk_panel_gemv`) and against the block-structured kernel for subgroup samples that are NOT plane rotations
+    (structure code 3 instead of 11): same numbers to rounding; ragged sizes, more subgroup samples than one staging pass holds."""
+    from liestationarykernels_b200 import ops
+    from liestationarykernels_b200.prior_approximation import RandomPhaseApproximation
+    from liestationarykernels_b200.spaces import Stiefel
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(order + avg)
+    space = Stiefel(5, 3, order=order, average_order=avg)
+    assert space._identity_block(space.h_samples) == 11
+    kern = EigenbasisSumKernel(MaternSpectralMeasure(9, 0.8, 2.5, 1.3), space).eval()
+    sampler = RandomPhaseApproximation(kern, phase_order=P)
+    x = space.rand(N)
+    with torch.no_grad():
+        fused = sampler(x)
+        feats = space._phase_features(x, sampler.phases, sampler._row_scales(), panel=True)
+        two_pass = ops.panel_matvec(feats, sampler.weights)
+        dense = sampler.make_embedding(x)
+        assert scaled_err(fused, two_pass) < 1e-13
+        assert scaled_err(fused, dense @ sampler.weights) < 1e-13
+        # the same samples with a structure the rotation kernel must refuse: scale R by 1 + 1e-9 (no longer a rotation)
+        h2 = space.h_samples.clone()
+        h2[:, 3:, 3:] *= 1.0 + 1e-9
+        space.h_samples = h2
+        assert space._identity_block(space.h_samples) == 3
+        general = sampler(x)
+        assert scaled_err(general, fused) < 1e-7 and not torch.equal(general, fused)
