@@ -356,7 +356,7 @@ def run_c4(ctx, steps, warmup, with_e2e=True):
     launches = (_lib.launches() - launches0) * steps // (steps + warmup)
     feat_ms = ctx.time_steps(features, max(steps, 2), 1)
     gram_ms = ctx.time_steps(gram, steps, 1)
-    samp_ms = ctx.time_steps(sample, max(steps, 3), 1)
+    samp_ms = ctx.time_steps(sample, max(steps, 10), 3)         # ms-scale call: enough repetitions to average out NCCL's lazy set-up
     res = {"value": N * N / (ms_step * 1e-3), "unit": "entries/s", "ms_per_step": ms_step, "launches": launches,
            "features_ms": feat_ms, "feature_pairs_per_s": N * P / (feat_ms * 1e-3), "gram_ms": gram_ms,
            "sampler": {"ms": samp_ms, "points_per_s": N / (samp_ms * 1e-3),
@@ -437,7 +437,7 @@ def run_c5(ctx, steps, warmup, which=("h3", "spd3"), with_e2e=True):
         launches = (_lib.launches() - launches0) * steps // (steps + warmup)
         feat_ms = ctx.time_steps(features, max(steps, 2), 1)
         gram_ms = ctx.time_steps(gram, steps, 1)
-        samp_ms = ctx.time_steps(sample, max(steps, 3), 1)
+        samp_ms = ctx.time_steps(sample, max(steps, 10), 3)         # ms-scale call: enough repetitions to average out NCCL's lazy set-up
         r = {"value": N * N / (ms_step * 1e-3), "unit": "entries/s", "ms_per_step": ms_step, "launches": launches,
              "features_ms": feat_ms, "features_per_s": N * m / (feat_ms * 1e-3), "gram_ms": gram_ms,
              "sampler": {"ms": samp_ms, "points_per_s": N / (samp_ms * 1e-3),

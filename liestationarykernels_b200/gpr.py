@@ -26,7 +26,10 @@ dtype = torch.float64
 
 
 def _dense(k):
-    return k.evaluate() if hasattr(k, "evaluate") else k
+    """dense covariance of a kernel result: a tensor, a LazyGram, or a real gpytorch LazyTensor / linear_operator"""
+    if hasattr(k, "evaluate"):
+        return k.evaluate()
+    return k.to_dense() if hasattr(k, "to_dense") and not isinstance(k, torch.Tensor) else k
 
 
 class _GaussianLogProb(torch.autograd.Function):

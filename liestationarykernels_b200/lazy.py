@@ -52,6 +52,40 @@ class LazyGram:
         return self.evaluate()[idx]
 
 
+def _gpytorch_classes():
+    """(matmul class, dense wrapper class) of an importable gpytorch: the 1.7-era `gpytorch.lazy` API the reference targets
+    (spectral_kernel.py:9) or its successor `linear_operator`; None when neither is installed (this image)."""
+    try:
+        from gpytorch.lazy import MatmulLazyTensor, NonLazyTensor
+        return MatmulLazyTensor, NonLazyTensor
+    except Exception:
+        pass
+    try:
+        from linear_operator.operators import DenseLinearOperator, MatmulLinearOperator
+        return MatmulLinearOperator, DenseLinearOperator
+    except Exception:
+        return None
+
+
+USE_GPYTORCH = True       # hand real gpytorch objects to callers when gpytorch is importable (set False to always get LazyGram)
+
+
+def as_reference_lazy(gram: "LazyGram"):
+    """What the reference returns, `MatmulLazyTensor(NonLazyTensor(Fx), NonLazyTensor(Fy).t())` (spectral_kernel.py:125-127,
+    195-197), as a REAL gpytorch / linear_operator object when that package is importable, so that gpytorch models consume
+    the kernel unchanged; the feature maps are handed over dense and row-major, which is gpytorch's layout (its matmul is then
+    cuBLAS, not the DMMA Gram kernel - use `LazyGram.evaluate()` / `USE_GPYTORCH = False` for that).  Without gpytorch: `gram`."""
+    classes = _gpytorch_classes() if USE_GPYTORCH else None
+    if classes is None or gram.left is None:
+        return gram
+    matmul_cls, dense_cls = classes
+    left = gram.left.to_dense()
+    if gram.scale != 1.0:
+        left = left * gram.scale
+    right = left if (gram.right is gram.left and gram.scale == 1.0) else gram.right.to_dense()
+    return matmul_cls(dense_cls(left), dense_cls(right).t())
+
+
 def _transpose(pm: ops.PanelMatrix) -> ops.PanelMatrix:
     return ops.PanelMatrix.from_dense(pm.to_dense().t().contiguous())
 
@@ -116,22 +150,25 @@ class _FourierGramFn(torch.autograd.Function):
     The lengthscale reaches lmd (scaled samples) and coeff (c-function) through ordinary torch autograd on the host."""
 
     @staticmethod
-    def forward(ctx, lmd, coeff, amp, manifold, funcs, x, y):
-        ctx.manifold, ctx.funcs, ctx.x, ctx.y = manifold, funcs, x, y
+    def forward(ctx, lmd, coeff, amp, manifold, funcs, x, y, grouped=False):
+        """grouped: x and y are already in group form (`manifold.to_group` applied: the pairwise differences of RandomSpectralKernel)"""
+        ctx.manifold, ctx.funcs, ctx.x, ctx.y, ctx.grouped = manifold, funcs, x, y, grouped
         ctx.save_for_backward(lmd, coeff, amp)
         s = float(amp.detach()) ** 0.5
-        px = manifold._features(manifold.to_group(x), funcs, s, "panel")
-        py = px if y is x else manifold._features(manifold.to_group(y), funcs, s, "panel")
+        group = (lambda t: t) if grouped else manifold.to_group
+        px = manifold._features(group(x), funcs, s, "panel")
+        py = px if y is x else manifold._features(group(y), funcs, s, "panel")
         return ops.gram(px, py)
 
     @staticmethod
     def backward(ctx, grad):
         lmd, coeff, amp = ctx.saved_tensors
         m, funcs, x, y = ctx.manifold, ctx.funcs, ctx.x, ctx.y
-        fx = m._features(m.to_group(x), funcs, 1.0, "complex")
-        fy = fx if y is x else m._features(m.to_group(y), funcs, 1.0, "complex")
-        dx = m._log_terms(x, funcs)                         # [N, m, R]
-        dy = dx if y is x else m._log_terms(y, funcs)
+        group = (lambda t: t) if ctx.grouped else m.to_group
+        fx = m._features(group(x), funcs, 1.0, "complex")
+        fy = fx if y is x else m._features(group(y), funcs, 1.0, "complex")
+        dx = m._log_terms(x, funcs, ctx.grouped)            # [N, m, R]
+        dy = dx if y is x else m._log_terms(y, funcs, ctx.grouped)
         g = grad.contiguous()
         pg, pgt = ops.PanelMatrix.from_dense(g), ops.PanelMatrix.from_dense(g.t().contiguous())
 
@@ -150,15 +187,15 @@ class _FourierGramFn(torch.autograd.Function):
         g_amp = a_k.sum().reshape(amp.shape)
         g_coeff = 2.0 * amp * a_k / coeff
         g_lmd = (-amp * (b_kr - c_kr)).reshape(lmd.shape)
-        return g_lmd, g_coeff, g_amp, None, None, None, None
+        return g_lmd, g_coeff, g_amp, None, None, None, None, None
 
 
 class DifferentiableFourierGram(LazyGram):
     """Lazy Gram of the Fourier-feature kernel on H^n / SPD(n) whose `evaluate()` carries hyper-parameter gradients."""
 
-    def __init__(self, manifold, funcs, x, y, lmd, coeff, amp):
+    def __init__(self, manifold, funcs, x, y, lmd, coeff, amp, grouped=False):
         self.manifold, self.funcs, self.x, self.y = manifold, funcs, x, y
-        self.lmd, self.coeff, self.amp = lmd, coeff, amp
+        self.lmd, self.coeff, self.amp, self.grouped = lmd, coeff, amp, grouped
         self.left = self.right = None
         self.scale = 1.0
 
@@ -167,7 +204,7 @@ class DifferentiableFourierGram(LazyGram):
         return torch.Size((self.x.shape[0], self.y.shape[0]))
 
     def evaluate(self, out=None):
-        k = _FourierGramFn.apply(self.lmd, self.coeff, self.amp, self.manifold, self.funcs, self.x, self.y)
+        k = _FourierGramFn.apply(self.lmd, self.coeff, self.amp, self.manifold, self.funcs, self.x, self.y, self.grouped)
         if out is not None:
             out.copy_(k.detach())
         return k
@@ -175,7 +212,7 @@ class DifferentiableFourierGram(LazyGram):
     to_dense = evaluate
 
     def t(self):
-        return DifferentiableFourierGram(self.manifold, self.funcs, self.y, self.x, self.lmd, self.coeff, self.amp)
+        return DifferentiableFourierGram(self.manifold, self.funcs, self.y, self.x, self.lmd, self.coeff, self.amp, self.grouped)
 
     def __getitem__(self, idx):
         return self.evaluate()[idx]

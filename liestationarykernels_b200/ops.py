@@ -44,6 +44,22 @@ def embed(plan: GroupPlan, x: torch.Tensor, side: str) -> torch.Tensor:
     return out
 
 
+def _embed_doubles(num: int, kg_total: int) -> int:
+    """= lsk_embed_buffer_doubles(num, kg_total): rows padded to 128, 256 doubles per (64-row panel, k-group)"""
+    return ((num + 127) // 128) * 2 * kg_total * 256
+
+
+def _pair_args(plan: GroupPlan):
+    """ctypes argument arrays of lsk_embed_points2 for a plan, built once (the hot call is launch-latency bound at small sizes)"""
+    cached = getattr(plan, "_pair_args", None)
+    if cached is None:
+        nseg = len(plan.segments_a)
+        cached = (nseg, (ctypes.c_int * nseg)(*[s[0] for s in plan.segments_a]), (ctypes.c_int * nseg)(*[s[1] for s in plan.segments_a]),
+                  (ctypes.c_int * nseg)(*[s[1] for s in plan.segments_b]), (ctypes.c_int * nseg)(*plan.group_begin))
+        plan._pair_args = cached
+    return cached
+
+
 def embed_pair(plan: GroupPlan, x: torch.Tensor, y: torch.Tensor):
     """Embeddings of both operands of `kernel(x, y)` with ONE launch (side A for x, side B for y)."""
     _lib.require_cuda()
@@ -52,13 +68,10 @@ def embed_pair(plan: GroupPlan, x: torch.Tensor, y: torch.Tensor):
     y = _as_matrix_batch(y, plan.n, plan.is_complex)
     if x.shape[0] == 0 or y.shape[0] == 0 or [s[0] for s in plan.segments_a] != [s[0] for s in plan.segments_b]:
         return embed(plan, x, "a"), embed(plan, y, "b")
-    nseg = len(plan.segments_a)
-    wedge = (ctypes.c_int * nseg)(*[s[0] for s in plan.segments_a])
-    part_a = (ctypes.c_int * nseg)(*[s[1] for s in plan.segments_a])
-    part_b = (ctypes.c_int * nseg)(*[s[1] for s in plan.segments_b])
-    begin = (ctypes.c_int * nseg)(*plan.group_begin)
-    ea = torch.empty(lib.lsk_embed_buffer_doubles(x.shape[0], plan.kg_total), dtype=F64, device=x.device)
-    eb = torch.empty(lib.lsk_embed_buffer_doubles(y.shape[0], plan.kg_total), dtype=F64, device=x.device)
+    nseg, wedge, part_a, part_b, begin = _pair_args(plan)
+    na, nb = _embed_doubles(x.shape[0], plan.kg_total), _embed_doubles(y.shape[0], plan.kg_total)
+    both = torch.empty(na + nb, dtype=F64, device=x.device)          # one allocation for the two operands
+    ea, eb = both[:na], both[na:]
     xr, yr = (torch.view_as_real(x), torch.view_as_real(y)) if plan.is_complex else (x, y)
     _lib.check(lib.lsk_embed_points2(_lib.ptr(xr), x.shape[0], part_a, _lib.ptr(ea), _lib.ptr(yr), y.shape[0], part_b,
                                      _lib.ptr(eb), plan.n, int(plan.is_complex), nseg, wedge, begin, plan.kg_total,

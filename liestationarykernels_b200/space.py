@@ -100,7 +100,14 @@ class LBEigenspace:
 
     @property
     def basis(self):
-        raise NotImplementedError("TranslatedCharactersBasis is outside the kernel/sampling path (SURVEY.md 2, row 3b)")
+        """Orthonormal basis of the eigenspace from translated characters (space.py:204-217, so.py:206-207, su.py:135-136);
+        built on first use (dim^2 translations, a dim^2 x dim^2 Gram and its Cholesky factor: for small irreps only)."""
+        if getattr(self, "_basis", None) is None:
+            self._basis = self.compute_basis()
+        return self._basis
+
+    def compute_basis(self):
+        return TranslatedCharactersBasis(representation=self)
 
 
 class CompactLieGroup(AbstractManifold, ABC):
@@ -170,6 +177,47 @@ class CompactLieGroup(AbstractManifold, ABC):
 
     def _chi_from_elements(self, position, x):
         return self._chi_from_gammas(position, self.torus_representative(x))
+
+
+class TranslatedCharactersBasis(torch.nn.Module):
+    """Orthonormal basis of the space of matrix coefficients of one irrep V: the dim(V)^2 functions x -> d chi(g_m x) for random
+    translations g_m, orthogonalised with the inverse Cholesky factor of their Gram matrix G[m, m'] = d chi(g_m g_m'^{-1})
+    (space.py:284-314; same RNG call, `manifold.rand(dim ** 2)`, same retry rule: up to three draws).
+
+    Not a hot path (the reference's EigenbasisKernel is the only caller and works for small irreps only: the Gram is
+    dim^2 x dim^2): batched torch ops on the GPU through the API-compatibility methods (`pairwise_embed`, `torus_representative`,
+    the weight-monomial character)."""
+
+    def __init__(self, *, representation):
+        super().__init__()
+        self.representation = representation
+        dim = self.representation.dimension
+        self.character = self.representation.phase_function
+        manifold = self.representation.manifold
+        attempts = 0
+        while True:
+            attempts += 1
+            self.translations = manifold.rand(dim ** 2)
+            try:
+                self._factorise()
+                break
+            except RuntimeError:
+                if attempts >= 3:
+                    raise
+
+    def _factorise(self):
+        """coeffs = inverse Cholesky factor of the Gram of the current translations (space.py:300-303)"""
+        manifold, dim = self.representation.manifold, self.representation.dimension
+        ratios = manifold.pairwise_embed(self.translations, self.translations)
+        gram = self.character.forward(ratios).reshape(dim ** 2, dim ** 2)
+        self.coeffs = torch.linalg.inv(torch.linalg.cholesky(gram))
+
+    def forward(self, x):
+        """[N, dim^2] complex: b_k(x_n) = sum_m coeffs[k, m] d chi(g_m x_n)"""
+        manifold = self.representation.manifold
+        x_translates = torch.matmul(self.translations.unsqueeze(0), x.unsqueeze(1))          # [N, dim^2, n, n]
+        characters = self.character.forward(manifold.torus_representative(x_translates))     # [N, dim^2]
+        return torch.matmul(self.coeffs, characters.to(self.coeffs.dtype).T).T
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -94,9 +94,9 @@ class HyperbolicSpace(NonCompactSymmetricSpace):
             lmd, shift = self.lb_eigenspaces.exp.lmd.detach() * (scale / scale.detach()), self.lb_eigenspaces.exp.shift
         return lmd, shift, self.c_function(lmd)
 
-    def _log_terms(self, x, funcs):
+    def _log_terms(self, x, funcs, grouped=False):
         """L[i, k] = log((1 - |x_i|^2) / |x_i - b_k|^2): dF_ik / dlmd_k = -i L_ik F_ik"""
-        pg, shift = self.to_group(x), funcs.exp.shift
+        pg, shift = (x if grouped else self.to_group(x)), funcs.exp.shift
         d2 = torch.sum(torch.square(pg[:, None, :] - shift[None, :, :]), dim=-1)
         return -(torch.log(1 - torch.sum(torch.square(pg), dim=1))[:, None] - torch.log(d2))[:, :, None]
 
@@ -203,10 +203,10 @@ class SymmetricPositiveDefiniteMatrices(NonCompactSymmetricSpace):
             lmd = self.lb_eigenspaces.exp.lmd.detach() * (inv_scale / inv_scale.detach())
         return lmd, shift, self.c_function_tanh(lmd)
 
-    def _log_terms(self, x, funcs):
+    def _log_terms(self, x, funcs, grouped=False):
         """la[i, k, r] = log a_r(U_i h_k^{-1}): dF_ik / dlmd_kr = i la_r F_ik  (CUDA kernel `lsk_spd_logdiag`)"""
         lib = _lib.load()
-        u = self.to_group(x).to(dtype).contiguous()
+        u = (x if grouped else self.to_group(x)).to(dtype).contiguous()
         hinv = self.inv(funcs.exp.shift)
         m = funcs.exp.lmd.shape[0]
         out = torch.empty((u.shape[0], m, self.n), dtype=dtype, device=u.device)

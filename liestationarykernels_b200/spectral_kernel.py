@@ -239,6 +239,35 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         self._ep_cache = {}
 
 
+class EigenbasisKernel(AbstractSpectralKernel):
+    """k(x, y) = sum_l a(lambda_l) sum_k f_{l,k}(x) conj(f_{l,k}(y)) over an explicit orthonormal basis of every eigenspace
+    (spectral_kernel.py:57-75; `eigenspace.basis` = TranslatedCharactersBasis on Lie groups).  Equal to EigenbasisSumKernel in
+    exact arithmetic (the basis functions of an irrep sum to d chi(x y^{-1})); it exists for API parity and as a cross-check,
+    and is usable for small irreps only (dim^2 basis functions, a dim^2 x dim^2 Cholesky per irrep).
+
+    The reference's forward has a shape slip: with `f_x = f(x).T` ([dim^2, N]) it accumulates `f_x @ f_y.T`, a
+    [dim^2, dim^2] matrix, into the [N, M] result, which only broadcasts when N = M = dim^2.  The evident intent -
+    `f(x) @ f(y)^H`, real part - is what is computed here."""
+
+    def __init__(self, measure, manifold):
+        super().__init__(measure, manifold)
+        point = self.manifold.id
+        self.normalizer = self.forward(point, point, normalize=False)[0, 0]
+
+    def forward(self, x, y=None, normalize=True):
+        if y is None:
+            y = x
+        cov = torch.zeros(len(x), len(y), dtype=dtype, device=x.device)
+        for eigenspace in self.manifold.lb_eigenspaces:
+            f = eigenspace.basis
+            f_x = f(x)                                   # [N, dim^2]
+            f_y = f_x if y is x else f(y)
+            cov = cov + self.measure(eigenspace.lb_eigenvalue) * (f_x @ f_y.conj().T).real
+        if normalize:
+            return cov / self.normalizer
+        return cov
+
+
 class RandomPhaseKernel(AbstractSpectralKernel):
     """Feature-map approximation with random phases (spectral_kernel.py:78-127):
        Phi[n, l*P + p] = sqrt(a_l / P) * Re phase_function_l(phase_p, x_n),   k = |sigma^2| / norm * Phi_x Phi_y^T."""
@@ -317,8 +346,8 @@ class RandomPhaseKernel(AbstractSpectralKernel):
         fx = self._features(x, scales, panel=True)
         fy = fx if y is x else self._features(y, scales, panel=True)
         scale = float(torch.abs(self.measure.variance[0]).item() / float(self.normalizer)) if normalize else 1.0
-        from .lazy import LazyGram
-        return LazyGram(fx, fy, scale)
+        from .lazy import LazyGram, as_reference_lazy
+        return as_reference_lazy(LazyGram(fx, fy, scale))
 
 
 def _rff_scale(kernel, normalize):
@@ -380,8 +409,8 @@ class RandomFourierFeatureKernel(AbstractSpectralKernel):
         s = _rff_scale(self, normalize)
         px = manifold._features(manifold.to_group(x), manifold.lb_eigenspaces, s, "panel")
         py = px if y is x else manifold._features(manifold.to_group(y), manifold.lb_eigenspaces, s, "panel")
-        from .lazy import LazyGram
-        return LazyGram(px, py, 1.0)
+        from .lazy import LazyGram, as_reference_lazy
+        return as_reference_lazy(LazyGram(px, py, 1.0))
 
 
 class RandomSpectralKernel(AbstractSpectralKernel):
@@ -399,13 +428,46 @@ class RandomSpectralKernel(AbstractSpectralKernel):
         point = self.manifold.rand()
         self.normalizer = self.forward(point, point, normalize=False)[0, 0]
 
+    def _differentiable(self, x, y, normalize):
+        """Forward with lengthscale / variance gradients (the reference's forward is plain torch and therefore differentiable:
+        spectral_kernel.py:140-161).  Same machinery as the feature-map kernel: the pairwise differences are the "points", the
+        identity is the only other point, K = Gram(F(diff), F(id)) through `lazy._FourierGramFn`.  Training mode mirrors the
+        reference's call order: features are generated, `compute_normalizer` draws a point and its nested forward generates them
+        AGAIN (a fresh draw on SPD(n), spd.py:28) - that last set serves both the normaliser and the covariance."""
+        from .lazy import DifferentiableFourierGram
+        from .spaces.noncompact import _SphericalFunctions
+        m, meas = self.manifold, self.measure
+        lmd, shift, coeff = m._differentiable_spectrum(meas, resample=self.training)
+        if self.training and normalize:
+            m.rand()                                                             # the point of compute_normalizer (RNG order)
+            lmd, shift, coeff = m._differentiable_spectrum(meas, resample=True)
+        funcs = _SphericalFunctions(lmd.detach(), shift, m, coeff.detach())
+        if self.training:
+            m.lb_eigenspaces = funcs
+        x_, y_ = m.to_group(x), m.to_group(y)
+        diff = m.pairwise_diff(x_, y_)
+        ident = m.to_group(m.id) if m.id.dim() == 3 else m.id
+        one = torch.ones((), dtype=dtype, device=lmd.device)
+        cov = DifferentiableFourierGram(m, funcs, diff, ident, lmd, coeff, one, grouped=True).evaluate()[:, 0].view(x.size()[0], y.size()[0])
+        if not normalize:
+            return cov
+        if self.training:
+            norm = (coeff * coeff).sum()                                         # the kernel at coinciding points: sum_k |F_k(id)|^2
+            self.normalizer = norm.detach()
+        else:
+            norm = torch.as_tensor(self.normalizer, dtype=dtype, device=lmd.device).detach()
+        return meas.variance[0] * cov / norm
+
     def forward(self, x, y=None, normalize=True):
+        if y is None:
+            y = x
+        if torch.is_grad_enabled() and hasattr(self.manifold, "_differentiable_spectrum") and \
+                (self.measure.lengthscale.requires_grad or self.measure.variance.requires_grad):
+            return self._differentiable(x, y, normalize)
         if self.training:
             self.manifold.generate_lb_eigenspaces(self.measure)
             if normalize:
                 self.compute_normalizer()
-        if y is None:
-            y = x
         manifold = self.manifold
         x_, y_ = manifold.to_group(x), manifold.to_group(y)
         diff = manifold.pairwise_diff(x_, y_)

@@ -633,6 +633,17 @@ def rff_kernel(space, measure, lmd, shift, x, y, normalizer=None):
     return px @ py.t().clone()
 
 
+def random_spectral_kernel(space, measure, lmd, shift, x, y, normalizer=None):
+    """spectral_kernel.py:140-161 (RandomSpectralKernel.forward): Re F(x_i y_j^{-1}) conj(F(id))^T; H^n only (`pairwise_diff`)."""
+    diff = space.pairwise_diff(space.to_group(x), space.to_group(y))
+    f_diff = space.features(diff, lmd, shift)
+    f_id = space.features(space.to_group(space.id), lmd, shift)
+    cov = (f_diff @ torch.conj(f_id).T).view(x.size()[0], y.size()[0]).real
+    if normalizer is not None:
+        return measure.variance[0] * cov / normalizer
+    return cov
+
+
 def rff_sample(space, measure, lmd, shift, w_re, w_im, x, normalizer):
     """prior_approximation.py:111-117."""
     f = space.features(space.to_group(x), lmd, shift) * torch.sqrt(torch.abs(measure.variance[0]))

@@ -283,6 +283,19 @@ def main(only=None):
                         features=feats, gram=gram, w_re=sampler.weights_real, w_im=sampler.weights_imag,
                         sample=sample, cov=cov))
 
+    # ------------------------------------------------------------------ TranslatedCharactersBasis (space.py:284-314) on small irreps
+    for name, cls, n, order in (("basis_so3", SO, 3, 3), ("basis_su2", SU, 2, 3), ("basis_su3", SU, 3, 3)):
+        if not want(name):
+            continue
+        torch.manual_seed(777)
+        space = cls(n, order=order)
+        x, y = space.rand(9), space.rand(7)
+        irreps = []
+        for eig in space.lb_eigenspaces:
+            basis = eig.basis                                   # draws dim^2 translations, factorises their Gram
+            irreps.append(dict(index=eig.index, dimension=eig.dimension, translations=basis.translations, coeffs=basis.coeffs,
+                               f_x=basis(x), f_y=basis(y)))
+        save(name, dict(group=cls.__name__, n=n, order=order, x=x, y=y, irreps=irreps))
 
 if __name__ == "__main__":
     main(sys.argv[1:] or None)

@@ -81,3 +81,12 @@ def test_error_strings_are_stateless_and_cover_the_codes():
         _lib.check(-2, "probe")
     assert lib.lsk_potrf_work_doubles(0) >= 0 and lib.lsk_potrf_work_doubles(300) > lib.lsk_potrf_work_doubles(0)
     assert lib.lsk_potri_work_doubles(-1) == -2 and lib.lsk_trsm_work_doubles(128, 5) > 0
+
+
+def test_python_embed_size_matches_the_library():
+    """ops._embed_doubles mirrors lsk_embed_buffer_doubles (the hot call computes it without a library round trip)"""
+    from liestationarykernels_b200 import _lib, ops
+    lib = _lib.load()
+    for num in (1, 63, 64, 127, 128, 129, 1000, 16384, 65536):
+        for kg in (1, 3, 11, 21, 4096):
+            assert ops._embed_doubles(num, kg) == lib.lsk_embed_buffer_doubles(num, kg)

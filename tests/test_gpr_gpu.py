@@ -314,3 +314,19 @@ def test_likelihood_and_mll_are_pure_and_idempotent():
     assert torch.allclose(noisy1.diagonal() - before.diagonal(), lik.noise.detach().expand(n), rtol=0, atol=1e-14)
     (a + b).backward()                                    # both graphs are intact
     assert torch.isfinite(kern.measure.lengthscale.grad).all() and torch.isfinite(lik.raw_noise.grad).all()
+
+
+@pytest.mark.parametrize("n,k", [(300, 24), (1000, 129), (517, 64)])
+def test_solve_with_many_right_hand_sides(n, k):
+    """A^{-1} B for a block of right-hand sides (dense-inverse + Gram path from 24 columns on) against the per-column sweeps and
+    against the residual"""
+    from liestationarykernels_b200.linalg import CholeskyFactor
+    torch.manual_seed(n + k)
+    a = _covariance(n, 5e-2)
+    f = CholeskyFactor(a)
+    b = torch.randn(n, k, dtype=torch.float64, device="cuda")
+    x = f.solve(b)
+    assert x.shape == (n, k)
+    assert ((a @ x - b).abs().max() / b.abs().max()).item() < 1e-10
+    cols = torch.stack([f.solve(b[:, c].contiguous()) for c in range(0, k, max(k // 5, 1))], dim=1)
+    assert (x[:, ::max(k // 5, 1)] - cols).abs().max().item() < 1e-10 * cols.abs().max().item()

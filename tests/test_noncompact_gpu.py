@@ -171,3 +171,62 @@ def test_spd_fourier_kernel_hyperparameter_gradients(kind, n, m, training):
     for ours, ref in ((meas.lengthscale.grad, om.lengthscale.grad), (meas.variance.grad, om.variance.grad)):
         assert ours is not None
         assert abs(ours.item() - ref.item()) < 1e-8 * max(1.0, abs(ref.item())), (ours.item(), ref.item())
+
+
+@pytest.mark.parametrize("kind,n,m", [("matern", 3, 48), ("heat", 2, 40)])
+def test_random_spectral_kernel_hyperparameter_gradients(kind, n, m):
+    """RandomSpectralKernel (the pairwise form, spectral_kernel.py:130-161) is plain torch in the reference and therefore
+    differentiable in lengthscale and variance; ours: value and both gradients against torch autograd through the oracle port."""
+    import lsk_oracle as orc
+    from liestationarykernels_b200.spaces import HyperbolicSpace
+    from liestationarykernels_b200.spectral_kernel import RandomSpectralKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure, SqExpSpectralMeasure
+    torch.manual_seed(41)
+    oh = orc.Hyperbolic(n, order=m)
+    om = orc.Measure(kind, n, 0.8, 1.5 if kind == "matern" else None, 1.6)
+    om.lengthscale.requires_grad_(True)
+    om.variance.requires_grad_(True)
+    nx, ny = 13, 9
+    x, y = oh.rand(nx) * 0.7, oh.rand(ny) * 0.7
+    lmd, shift = oh.generate(om)
+    norm = (oh.c_function(lmd) ** 2).sum()                   # the kernel at coinciding points: sum_k |F_k(id)|^2
+    k_ref = orc.random_spectral_kernel(oh, om, lmd, shift, x, y, norm)
+    g_out = torch.randn(nx, ny, dtype=torch.float64)
+    (k_ref * g_out).sum().backward()
+    space = HyperbolicSpace(n, order=m)
+    space.normalized_lmd, space.shift = oh.normalized_lmd.cuda(), oh.shift.cuda()      # same-tensor rule
+    meas = MaternSpectralMeasure(n, 0.8, 1.5, 1.6) if kind == "matern" else SqExpSpectralMeasure(n, 0.8, 1.6)
+    kern = RandomSpectralKernel(meas, space)
+    kern.train()
+    k = kern(x.cuda(), y.cuda())
+    assert k.shape == (nx, ny) and scaled_err(k.detach().cpu(), k_ref.detach()) < 1e-10
+    assert abs(float(kern.normalizer) - norm.item()) < 1e-10 * abs(norm.item())
+    (k * g_out.cuda()).sum().backward()
+    for ours, ref in ((meas.lengthscale.grad, om.lengthscale.grad), (meas.variance.grad, om.variance.grad)):
+        assert ours is not None
+        assert abs(ours.item() - ref.item()) < 1e-8 * max(1.0, abs(ref.item())), (ours.item(), ref.item())
+    kern.eval()
+    with torch.no_grad():
+        plain = kern(x.cuda(), y.cuda())
+    assert scaled_err(plain.cpu(), k_ref.detach()) < 1e-10
+
+
+def test_random_spectral_kernel_on_spd_is_differentiable():
+    from liestationarykernels_b200.spaces import SymmetricPositiveDefiniteMatrices
+    from liestationarykernels_b200.spectral_kernel import RandomSpectralKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(43)
+    space = SymmetricPositiveDefiniteMatrices(2, order=32)
+    meas = MaternSpectralMeasure(space.dim, 0.9, 1.5, 1.3)
+    kern = RandomSpectralKernel(meas, space)
+    kern.eval()
+    x = space.rand(7)
+    k = kern(x, x)
+    assert k.requires_grad and torch.isfinite(k).all()
+    with torch.no_grad():
+        plain = kern(x, x)
+    assert scaled_err(k.detach(), plain) < 1e-12
+    k.sum().backward()
+    assert torch.isfinite(meas.lengthscale.grad).all()
+    # variance enters linearly: dK/dvar = K / var
+    assert abs(meas.variance.grad.item() - (plain.sum() / 1.3).item()) < 1e-9 * abs(plain.sum().item())

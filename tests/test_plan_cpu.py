@@ -112,3 +112,44 @@ def test_sphere_dimensions_and_zonal_rows_at_the_pole():
         assert np.allclose(at_one, dims, rtol=1e-12, atol=0)
         ep = plan.epilogue(np.ones(len(degrees)), 1.0)
         assert ep.nforms == 1 and ep.nvars == 1 and ep.nterms == max(degrees) + 1
+
+
+def test_lazy_results_become_real_gpytorch_objects_when_gpytorch_is_importable(monkeypatch):
+    """spectral_kernel.py:125-127 returns `gpytorch.lazy.MatmulLazyTensor(NonLazyTensor(Fx), NonLazyTensor(Fy).t())`; gpytorch is
+    not in the image, so a stand-in module with that API is injected: `as_reference_lazy` must build exactly that object from the
+    panel-major feature maps (dense, scale folded into the left factor), and fall back to LazyGram without the package."""
+    import sys
+    import types
+    import torch
+    from liestationarykernels_b200 import lazy, ops
+
+    class NonLazyTensor:
+        def __init__(self, t):
+            self.tensor = t
+
+        def t(self):
+            return NonLazyTensor(self.tensor.t())
+
+    class MatmulLazyTensor:
+        def __init__(self, a, b):
+            self.left, self.right = a, b
+
+        def evaluate(self):
+            return self.left.tensor @ self.right.tensor
+
+    torch.manual_seed(0)
+    a, b = torch.randn(70, 24, dtype=torch.float64), torch.randn(33, 24, dtype=torch.float64)
+    gram = lazy.LazyGram(ops.PanelMatrix.from_dense(a), ops.PanelMatrix.from_dense(b), 0.25)
+    monkeypatch.setitem(sys.modules, "gpytorch", None)
+    monkeypatch.setitem(sys.modules, "linear_operator", None)
+    assert lazy.as_reference_lazy(gram) is gram                       # nothing importable: the stand-in object
+    mod, sub = types.ModuleType("gpytorch"), types.ModuleType("gpytorch.lazy")
+    sub.NonLazyTensor, sub.MatmulLazyTensor = NonLazyTensor, MatmulLazyTensor
+    mod.lazy = sub
+    monkeypatch.setitem(sys.modules, "gpytorch", mod)
+    monkeypatch.setitem(sys.modules, "gpytorch.lazy", sub)
+    real = lazy.as_reference_lazy(gram)
+    assert isinstance(real, MatmulLazyTensor)
+    assert torch.allclose(real.evaluate(), 0.25 * a @ b.T, rtol=1e-14, atol=1e-14)
+    monkeypatch.setattr(lazy, "USE_GPYTORCH", False)
+    assert lazy.as_reference_lazy(gram) is gram
