@@ -529,6 +529,32 @@ extern "C" int lsk_embed_points2(const void* x, long long num_x, const int* part
 extern "C" int lsk_version(void) { return LSK_VERSION; }
 
 // Stateless: the text for a return code of any entry point (0 ok, < 0 LSK_E*, > 0 cudaError_t).
+// ---- snapshot of a few device scalars into host-mapped pinned memory ------------------------------------------------------
+namespace lsk {
+struct SnapshotArgs { const double* src[LSK_MAX_SNAPSHOT]; };
+
+__global__ void __launch_bounds__(32)
+snapshot_kernel(const __grid_constant__ SnapshotArgs a, int n, double* __restrict__ dst, unsigned long long seq) {
+    pdl_launch_dependents();
+    pdl_wait();                                   // the scalars may have been written by the kernel launched just before
+    const int t = threadIdx.x;
+    if (t < n) dst[t] = *a.src[t];
+    __threadfence_system();
+    __syncwarp();
+    if (t == 0) *reinterpret_cast<volatile unsigned long long*>(dst + LSK_MAX_SNAPSHOT) = seq;
+}
+}  // namespace lsk
+
+extern "C" int lsk_snapshot_doubles(const void* const* src, int n, void* dst_host_mapped, unsigned long long seq, void* stream) {
+    using namespace lsk;
+    if (!src || !dst_host_mapped) return LSK_EARG;
+    if (n < 0 || n > LSK_MAX_SNAPSHOT) return LSK_ESIZE;
+    SnapshotArgs a = {};
+    for (int i = 0; i < n; ++i) { if (!src[i]) return LSK_EARG; a.src[i] = static_cast<const double*>(src[i]); }
+    return (int)launch_pdl(snapshot_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), a, n,
+                           static_cast<double*>(dst_host_mapped), seq);
+}
+
 extern "C" const char* lsk_error_string(int code) {
     switch (code) {
     case 0: return "ok";

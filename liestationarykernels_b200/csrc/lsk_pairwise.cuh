@@ -6,6 +6,7 @@
 #define LSK_MAX_VARS 5
 #define LSK_MAX_COEF 400
 #define LSK_MAX_ROWS 24
+#define LSK_MAX_SNAPSHOT 7
 #define LSK_STAIR_MAX_ROWS 12    // STAIR2: rows sit at a fixed stride of LSK_STAIR_STRIDE coefficients
 #define LSK_STAIR_STRIDE 16
 
