@@ -81,13 +81,14 @@ typedef struct LskEpilogue {
 
 int lsk_version(void);
 
-/* Stream-ordered snapshot of up to LSK_MAX_SNAPSHOT device doubles into host-mapped pinned memory:
- *   dst[i] = *src[i] (i < n), then dst[LSK_MAX_SNAPSHOT] (read as uint64) = seq, after a system-scope fence.
- * One 32-thread kernel, no copy engine, no event: the host polls the sequence word.  The Python layer uses it to verify, without
- * draining the stream, that the kernel hyper-parameters (reference spectral_measure.py:20-21: device-resident nn.Parameters that
- * the reference re-reads on every call) still have the values the cached coefficient block was built from.
+/* Stream-ordered snapshot of up to LSK_MAX_SNAPSHOT device doubles into host-mapped pinned memory: slot i (16 bytes, one store)
+ *   dst[2 i] = *src[i],   dst[2 i + 1] (read as uint64) = bits(*src[i]) ^ (seq * 0x9E3779B97F4A7C15 + 0x7F4A7C159E3779B9).
+ * One 32-thread kernel, no copy engine, no event, no system-scope fence: the host polls until every slot's tag matches its value
+ * for the sequence number it passed.  The Python layer uses it to verify, without draining the stream, that the kernel
+ * hyper-parameters (reference spectral_measure.py:20-21: device-resident nn.Parameters that the reference re-reads on every
+ * call) still have the values the cached coefficient block was built from.
  * src: HOST array of n device pointers; dst_host_mapped: pinned host memory (cudaHostAlloc / torch pin_memory) of
- * LSK_MAX_SNAPSHOT + 1 doubles, addressed by its host pointer (unified addressing). */
+ * 2 * LSK_MAX_SNAPSHOT doubles, 16-byte aligned, addressed by its host pointer (unified addressing). */
 #define LSK_MAX_SNAPSHOT 7
 int lsk_snapshot_doubles(const void* const* src, int n, void* dst_host_mapped, unsigned long long seq, void* stream);
 

@@ -5,6 +5,8 @@ The forward passes do not materialise anything of size N*M except the result: se
 from __future__ import annotations
 
 import ctypes
+import os
+import time
 
 import numpy as np
 import torch
@@ -14,6 +16,10 @@ from .space import AbstractManifold, CompactLieGroup
 from .spectral_measure import AbstractSpectralMeasure
 
 dtype = torch.float64
+# snapshot polling (`EigenbasisSumKernel._finish_hyper_read`): spin this long, then sleep in slices.  Measured on 8 GPUs (one rank per
+# GPU, 0.31 ms steps): pure spinning keeps every rank within 0.5 % of the others; sleeping after 40 us costs the slowest rank 3 %.
+SPIN_SECONDS = float(os.environ.get("LSK_SPIN_US", "5000")) * 1e-6
+SLEEP_SECONDS = float(os.environ.get("LSK_SLEEP_US", "20")) * 1e-6
 
 
 class AbstractSpectralKernel(torch.nn.Module):
@@ -210,8 +216,8 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
             elif t is not None:
                 host.append(float(t))
         if self._pinned is None:
-            self._pinned = torch.zeros(8, dtype=dtype).pin_memory()
-            self._pinned_np = self._pinned.numpy()
+            self._pinned = torch.zeros(16, dtype=dtype).pin_memory()
+            self._pinned_np = self._pinned.numpy().view("uint64")
             self._seq = 0
         self._seq += 1
         lib = _lib.load()
@@ -221,17 +227,28 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         return (len(ptrs), host, normalize, self._seq)
 
     def _finish_hyper_read(self, pending):
+        """Poll the pinned slots until every [value, tag] pair is consistent for this call's sequence number (see lsk.h)."""
         n, host, normalize, seq = pending
-        view = self._pinned_np
-        seq_word = view[7:8].view("uint64")
-        spins = 0
-        while int(seq_word[0]) != seq:                        # written by the snapshot kernel after a system-scope fence
-            spins += 1
-            if spins > 2000000:                                # never observed; keeps a lost update from hanging the host
-                torch.cuda.current_stream().synchronize()
-                if int(seq_word[0]) != seq:
+        words = self._pinned_np
+        key = (seq * 0x9E3779B97F4A7C15 + 0x7F4A7C159E3779B9) & 0xFFFFFFFFFFFFFFFF
+        # Spin (the wait is at most one call of GPU work), then sleep in short slices if the queue ahead of this call is long.
+        t_start = time.perf_counter()
+        t_spin = t_start + SPIN_SECONDS
+        while True:
+            vals = [int(words[2 * t]) for t in range(n)]
+            if all((vals[t] ^ key) == int(words[2 * t + 1]) for t in range(n)):
+                break
+            now = time.perf_counter()
+            if now > t_spin:
+                if now - t_start > 2.0:                        # never observed; keeps a lost update from hanging the host
+                    torch.cuda.current_stream().synchronize()
+                    vals = [int(words[2 * t]) for t in range(n)]
+                    if all((vals[t] ^ key) == int(words[2 * t + 1]) for t in range(n)):
+                        break
                     raise _lib.LskError("hyper-parameter snapshot did not arrive")
-        return (normalize, self.form) + tuple([float(v) for v in view[:n]] + host)
+                time.sleep(SLEEP_SECONDS)
+        floats = np.array(vals, dtype=np.uint64).view(np.float64).tolist() if n else []
+        return (normalize, self.form) + tuple(floats + host)
 
     def _epilogue(self, normalize):
         """Coefficient block for the current hyper-parameters.  The cache is keyed on the parameter VALUES, read back on
