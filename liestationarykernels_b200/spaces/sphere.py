@@ -78,8 +78,51 @@ class SphereLBEigenspace(LBEigenspace):
 
     @property
     def basis(self):
-        raise NotImplementedError("NormalizedSphericalFunctions needs the `spherical_harmonics` package (sphere.py:133-143); "
-                                  "it is outside the kernel / sampling path")
+        """Orthonormal basis of the spherical harmonics of this degree (sphere.py:126-141), built on first use."""
+        if getattr(self, "_basis", None) is None:
+            self._basis = NormalizedSphericalFunctions(self.manifold.dim, self.index, self.phase_function, self.dimension)
+        return self._basis
+
+
+class NormalizedSphericalFunctions(torch.nn.Module):
+    """An orthonormal basis of the degree-`degree` spherical harmonics on S^dim (sphere.py:133-141).
+
+    The reference delegates to `spherical_harmonics.SphericalHarmonicsLevel` (vdutor/SphericalHarmonics, absent from the image),
+    whose published construction is: take a fundamental system v_1..v_N of N = dim H_l points, form the Gram matrix of the zonal
+    functions G_ij = Z_l(<v_i, v_j>), factor G = L L^T, and return Y(x) = L^{-1} [Z_l(<v_i, x>)]_i.  Restated here with
+    Z_l = this package's phase function (N_l C_l(t) / C_l(1), so that sum_k Y_k(x) Y_k(y) = Z_l(<x, y>), the addition theorem).
+    That package ships precomputed, optimised fundamental systems; here the system is chosen greedily (pivoted Cholesky over a
+    fixed pseudo-random candidate set, its own generator: the global RNG is not touched).  A different fundamental system gives a
+    different orthonormal basis of the SAME space, so basis values are not comparable entry by entry with the reference's, only
+    basis-independent quantities are (the sum over the basis, i.e. everything a kernel uses)."""
+
+    def __init__(self, dimension, degree, phase_function, num_harmonics):
+        super().__init__()
+        self.dimension, self.degree, self.zonal, self.num = dimension, degree, phase_function, int(num_harmonics)
+        dev = cuda_device()
+        gen = torch.Generator(device="cpu").manual_seed(1000003 * dimension + degree)
+        cand = torch.randn(4 * self.num + 64, dimension + 1, generator=gen, dtype=dtype)
+        cand = (cand / torch.linalg.norm(cand, dim=1, keepdim=True)).to(dev)
+        gram = self.zonal(cand @ cand.T)
+        # greedy pivoted Cholesky: pick the candidate with the largest remaining diagonal
+        diag = torch.diagonal(gram).clone()
+        rows = torch.zeros((self.num, cand.shape[0]), dtype=dtype, device=dev)
+        chosen = []
+        for k in range(self.num):
+            j = int(torch.argmax(diag))
+            chosen.append(j)
+            r = (gram[j] - rows[:k, j] @ rows[:k]) / torch.sqrt(diag[j])
+            rows[k] = r
+            diag = diag - r * r
+            diag[chosen] = -1.0
+        self.fundamental_system = cand[chosen].contiguous()
+        g = self.zonal(self.fundamental_system @ self.fundamental_system.T)
+        self.chol_inv = torch.linalg.inv(torch.linalg.cholesky(g))
+
+    def forward(self, x):
+        """[N, num_harmonics]"""
+        z = self.zonal(self.fundamental_system @ x.to(dtype).T)          # [num, N]
+        return (self.chol_inv @ z).T
 
 
 class _ZonalPlan(GroupPlan):

@@ -297,5 +297,35 @@ def main(only=None):
                                f_x=basis(x), f_y=basis(y)))
         save(name, dict(group=cls.__name__, n=n, order=order, x=x, y=y, irreps=irreps))
 
+    # ------------------------------------------------------------------ GP regression step (examples/gpr_model.py:26-39, 59-66)
+    # covariance and its hyper-parameter gradients from the REAL reference kernel (plain torch, differentiable); marginal likelihood
+    # and posterior by the LAPACK restatement of gpytorch's dense path (oracle gp_*; gpytorch itself is absent: see lsk_oracle.py)
+    import lsk_oracle as orc
+    for name, cls, n, order, mspec in (("gp_so3_matern", SO, 3, 10, dict(kind="matern", dim=3, lengthscale=0.8, nu=1.5, variance=1.7)),
+                                       ("gp_su3_heat", SU, 3, 8, dict(kind="heat", dim=8, lengthscale=1.1, variance=0.9))):
+        if not want(name):
+            continue
+        torch.manual_seed(4242)
+        space = cls(n, order=order)
+        meas = measure_of(mspec)
+        kern = EigenbasisSumKernel(meas, space)
+        kern.train()
+        n_train, n_test = 48, 12
+        x, xs = space.rand(n_train), space.rand(n_test)
+        targets = torch.randn(n_train, dtype=torch.float64)
+        raw_noise = torch.tensor([0.3], dtype=torch.float64, requires_grad=True)
+        const = torch.tensor([0.2], dtype=torch.float64, requires_grad=True)
+        k_train = kern(x)                                              # training mode: normaliser recomputed (consumes RNG)
+        loss = -orc.gp_log_marginal(k_train, orc.gp_noise(raw_noise)[0], const.expand(n_train), targets)
+        loss.backward()
+        kern.eval()
+        with torch.no_grad():
+            k_eval, k_star, k_ss = kern(x), kern(x, xs), kern(xs)
+            mean, cov = orc.gp_posterior(k_eval, k_star, k_ss, orc.gp_noise(raw_noise)[0], const.detach(), targets)
+        save(name, dict(group=cls.__name__, n=n, order=order, measure=mspec, x=x, xs=xs, targets=targets, raw_noise=raw_noise.detach(),
+                        constant=const.detach(), k_train=k_train, loss=loss, grad_lengthscale=meas.lengthscale.grad,
+                        grad_variance=meas.variance.grad, grad_raw_noise=raw_noise.grad, grad_constant=const.grad,
+                        eval_normalizer=kern.normalizer, posterior_mean=mean, posterior_cov=cov))
+
 if __name__ == "__main__":
     main(sys.argv[1:] or None)

@@ -49,3 +49,26 @@ def test_eigenbasis_kernel_equals_eigenbasis_sum_kernel(group, n, order):
         assert (a - b).abs().max().item() < 1e-8
         kxx = explicit(x)
         assert torch.allclose(kxx, kxx.T, atol=1e-10) and torch.allclose(kxx.diagonal(), torch.ones(11, dtype=torch.float64, device="cuda"), atol=1e-8)
+
+
+@pytest.mark.parametrize("cls,n,order", [("Sphere", 2, 5), ("Sphere", 3, 4), ("Sphere", 5, 3), ("ProjectiveSpace", 2, 3)])
+def test_spherical_harmonics_basis_and_eigenbasis_kernel_on_the_sphere(cls, n, order):
+    """`eigenspace.basis` on S^n / RP^n (NormalizedSphericalFunctions, sphere.py:126-141): the right number of functions, the
+    addition theorem sum_k Y_k(x) Y_k(y) = Z_l(<x, y>) (the basis-independent statement; the reference's basis comes from the
+    absent `spherical_harmonics` package and its own fundamental system), and EigenbasisKernel = EigenbasisSumKernel."""
+    from liestationarykernels_b200 import spaces
+    from liestationarykernels_b200.spectral_kernel import EigenbasisKernel, EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(8)
+    space = getattr(spaces, cls)(n, order=order)
+    state = torch.random.get_rng_state()
+    x, y = space.rand(13), space.rand(9)
+    for eig in space.lb_eigenspaces:
+        yx, yy = eig.basis(x), eig.basis(y)
+        assert yx.shape == (13, eig.dimension)
+        want = eig.phase_function((x @ y.T).reshape(-1)).reshape(13, 9)
+        assert (yx @ yy.T - want).abs().max().item() < 1e-9 * max(1.0, want.abs().max().item())
+    meas = MaternSpectralMeasure(space.dim, 0.8, 2.5, 1.0)
+    a = EigenbasisKernel(meas, space)(x, y)
+    b = EigenbasisSumKernel(meas, space).eval()(x, y)
+    assert (a - b).abs().max().item() < 1e-9

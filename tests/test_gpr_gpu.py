@@ -330,3 +330,49 @@ def test_solve_with_many_right_hand_sides(n, k):
     assert ((a @ x - b).abs().max() / b.abs().max()).item() < 1e-10
     cols = torch.stack([f.solve(b[:, c].contiguous()) for c in range(0, k, max(k // 5, 1))], dim=1)
     assert (x[:, ::max(k // 5, 1)] - cols).abs().max().item() < 1e-10 * cols.abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["gp_so3_matern", "gp_su3_heat"])
+def test_gp_step_against_committed_golden(name):
+    """One training loss with all four gradients and the eval-mode posterior against committed fixtures: covariance and its
+    hyper-parameter derivatives from the REAL reference kernel (torch autograd through its forward), marginal likelihood and
+    posterior from the LAPACK restatement of gpytorch's dense path (`oracle/make_golden.py`, section GP regression step)."""
+    from conftest import load_golden
+    from liestationarykernels_b200 import gpr
+    from liestationarykernels_b200.spaces import SO, SU
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure, SqExpSpectralMeasure
+    g = load_golden(name)
+    ms = g["measure"]
+    space = (SO if g["group"] == "SO" else SU)(g["n"], order=g["order"])
+    meas = MaternSpectralMeasure(ms["dim"], ms["lengthscale"], ms["nu"], ms["variance"]) if ms["kind"] == "matern" else \
+        SqExpSpectralMeasure(ms["dim"], ms["lengthscale"], ms["variance"])
+    kern = EigenbasisSumKernel(meas, space)
+    lik = gpr.GaussianLikelihood(device="cuda")
+    x, xs, targets = g["x"].cuda(), g["xs"].cuda(), g["targets"].cuda()
+    n = x.shape[0]
+    flat = (torch.view_as_real(x) if torch.is_complex(x) else x).reshape(n, -1)
+    shape = (g["n"], g["n"], 2) if torch.is_complex(x) else (g["n"], g["n"])
+    model = gpr.ExactGPModel(flat, targets, lik, kern, space, point_shape=shape)
+    if torch.is_complex(x):
+        model._points = lambda t: torch.view_as_complex(t.view(t.shape[0], g["n"], g["n"], 2).contiguous())
+    with torch.no_grad():
+        lik.raw_noise.copy_(g["raw_noise"].cuda())
+        model.mean_module.constant.copy_(g["constant"].cuda())
+    model.train()
+    out = model(flat)
+    assert (out._base.detach().cpu() - g["k_train"].detach()).abs().max().item() < 1e-10
+    loss = -gpr.ExactMarginalLogLikelihood(lik, model)(out, targets)
+    loss.backward()
+    assert abs(loss.item() - g["loss"].item()) <= 1e-10 * abs(g["loss"].item())
+    for ours, ref in ((meas.lengthscale.grad, g["grad_lengthscale"]), (meas.variance.grad, g["grad_variance"]),
+                      (lik.raw_noise.grad, g["grad_raw_noise"]), (model.mean_module.constant.grad, g["grad_constant"])):
+        assert abs(ours.item() - ref.item()) <= 1e-8 * max(1e-3, abs(ref.item())), (ours.item(), ref.item())
+    model.eval()
+    kern.eval()
+    kern.normalizer = g["eval_normalizer"].detach().cuda()
+    xs_flat = (torch.view_as_real(xs) if torch.is_complex(xs) else xs).reshape(xs.shape[0], -1)
+    with torch.no_grad():
+        pred = model(xs_flat)
+    assert (pred.mean.cpu() - g["posterior_mean"]).abs().max().item() <= 1e-9 * max(1.0, g["posterior_mean"].abs().max().item())
+    assert (pred.covariance_matrix.cpu() - g["posterior_cov"]).abs().max().item() <= 1e-9
