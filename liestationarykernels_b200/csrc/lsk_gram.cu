@@ -15,7 +15,8 @@
 //   * tiles are handed out in column bands of ~1536 columns, row-major inside a band, so the CTAs of one wave share
 //     ~12 x 12 tiles worth of operand panels in L2 instead of 1 x 148 (the generic order re-reads B from HBM for every row tile:
 //     ncu at 8192^2 x 16384: 63.6 GB of DRAM reads for 2.1 GB of operands, profiles/gram_ncu_summary_r02.json);
-//   * NT = 4 instantiation: 128 x 128 tiles (16 flop per byte staged instead of 10.7);
+//   * NT = 4 instantiation: 128 x 128 tiles (16 flop per byte staged instead of 10.7, 0.5 fragment loads per DMMA instead of 0.75);
+//     its consumers need ~110 registers, which 17 warps do not leave (96): it runs with a producer WARPGROUP and `setmaxnreg`;
 //   * symmetric mode (A and B are the same points): only tiles that reach the diagonal or lie above it, mirrored on store.
 #include <cstdlib>
 #include "lsk_common.cuh"
@@ -28,6 +29,11 @@ constexpr int KGS = 8;                              // k-groups (of 4 doubles) p
 constexpr int PANEL_STAGE = KGS * PANEL * 4;        // one 64-row panel, one stage: 2048 doubles = 16 KB
 constexpr int CONS_WARPS = 16;
 constexpr int THREADS_G = (CONS_WARPS + 1) * 32;    // + the producer warp
+// 128 x 128 tiles need ~110 registers per consumer thread; 17 warps leave 96 (five warps on one sub-partition).  That variant runs
+// with a whole producer WARPGROUP (20 warps, 96 registers each at launch) and moves registers from it to the consumers:
+// 4 x 32 x 24 + 16 x 32 x 112 = 60 416 <= 640 x 96.
+constexpr int THREADS_G4 = (CONS_WARPS + 4) * 32;
+constexpr int CONS_REGS_G4 = 112, PROD_REGS_G4 = 24;
 constexpr int TILE_SLOTS = 8;                       // ring of tile descriptors (producer -> consumers)
 
 template <int NT> struct Cfg {
@@ -50,7 +56,7 @@ __host__ __device__ inline long long count_tiles(int tiles_r, int tiles_c) {
 }
 
 template <int NT, bool SYM>
-__global__ void __launch_bounds__(THREADS_G, 1)
+__global__ void __launch_bounds__(NT == 4 ? THREADS_G4 : THREADS_G, 1)
 gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_rows, int n_cols, int kg_stride, int kg_len,
             double* __restrict__ out, long long ld_out, double scale, long long n_tiles)
 {
@@ -74,9 +80,13 @@ gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
     __syncthreads();
     pdl_wait();
 
-    if (warp == CONS_WARPS) {
+    if constexpr (NT == 4) {
+        if (warp >= CONS_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS_G4));
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS_G4));
+    }
+    if (warp >= CONS_WARPS) {
         // ===================== producer warp: one lane owns the ring and the tile order =====================
-        if (lane != 0) return;
+        if (warp != CONS_WARPS || lane != 0) return;
         // band state of the tile order: tiles [band_first, band_first + band_count) lie in column tiles [c0, c0 + w)
         int band = 0, c0 = 0, w = min(C::BAND, tiles_c);
         long long band_first = 0;
@@ -268,7 +278,7 @@ static int launch(const double* A, const double* B, int n_rows, int n_cols, int 
     const long long tiles = count_tiles<NT, SYM>(tiles_r, tiles_c);
     const int grid = (int)(tiles < sms ? tiles : sms);
     if ((tiles + grid - 1) / grid > 0x7fffffffLL) return LSK_ESIZE;
-    return (int)launch_pdl(kern, dim3(grid), dim3(THREADS_G), (size_t)C::SMEM_BYTES, stream, A, B, n_rows, n_cols, kg_stride, kg_len,
+    return (int)launch_pdl(kern, dim3(grid), dim3(NT == 4 ? THREADS_G4 : THREADS_G), (size_t)C::SMEM_BYTES, stream, A, B, n_rows, n_cols, kg_stride, kg_len,
                            out, ld_out, scale, tiles);
 }
 
@@ -279,8 +289,10 @@ static int launch(const double* A, const double* B, int n_rows, int n_cols, int 
 int gram_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_stride, int kg_len, double* out, long long ld_out,
                 double scale, bool symmetric, int sms, cudaStream_t stream) {
     static const int forced = [] { const char* s = getenv("LSK_GRAM_TILE"); return s ? atoi(s) : 0; }();
-    // 128 x 64 tiles by default: the 128 x 128 instantiation needs more than the 96 registers that 17 warps leave per thread
-    int nt = 2;
+    // 128 x 128 tiles (two thirds of the fragment loads and 25 % less L2 -> SM traffic per flop: 36.0-36.4 against 35.8-36.2 TFLOP/s)
+    // once the problem fills at least four waves of them; smaller problems keep the finer 128 x 64 grain
+    const long long t128 = (long long)((n_rows + 127) / 128) * ((n_cols + 127) / 128);
+    int nt = (t128 >= 4ll * sms) ? 4 : 2;
     if (forced == 2 || forced == 4) nt = forced;
     if (symmetric) {
         if (nt == 4) return gram::launch<4, true>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
