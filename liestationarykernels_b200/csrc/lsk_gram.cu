@@ -55,8 +55,11 @@ __host__ __device__ inline long long count_tiles(int tiles_r, int tiles_c) {
     return n;
 }
 
-template <int NT, bool SYM>
-__global__ void __launch_bounds__(NT == 4 ? THREADS_G4 : THREADS_G, 1)
+// MODE 0: out = scale * A B^T (SYM: upper triangle of tiles, mirrored);  MODE 1: out += scale * A B^T in place (SYM: the tiles
+// that reach the diagonal or lie above it, nothing mirrored) - the rank-k update of the blocked Cholesky (EPI_SYRK).  The old
+// entries of a tile are requested when the tile starts and consumed after its DMMA phase.
+template <int NT, bool SYM, int MODE>
+__global__ void __launch_bounds__((NT == 4 || MODE == 1) ? THREADS_G4 : THREADS_G, 1)
 gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_rows, int n_cols, int kg_stride, int kg_len,
             double* __restrict__ out, long long ld_out, double scale, long long n_tiles)
 {
@@ -80,7 +83,7 @@ gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
     __syncthreads();
     pdl_wait();
 
-    if constexpr (NT == 4) {
+    if constexpr (NT == 4 || MODE == 1) {
         if (warp >= CONS_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS_G4));
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS_G4));
     }
@@ -174,6 +177,27 @@ gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
         mbar_wait(&full_bar[stage], phase);
         const int2 desc = tile_desc[k % TILE_SLOTS];
         load_frags(s_base + (uint32_t)stage * STAGE_BYTES, 0, fa[0], fb[0]);
+        double prev[MODE == 1 ? 4 : 1][MODE == 1 ? NT : 1][2];
+        if constexpr (MODE == 1) {
+            const int r_base = desc.x * BM + wr * 32 + (lane >> 2), c_base = desc.y * BNT + wc * (8 * NT) + 2 * (lane & 3);
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const int row = r_base + m * 8, col = c_base + n * 8;
+                    prev[m][n][0] = 0.0; prev[m][n][1] = 0.0;
+                    if (row < n_rows && col < n_cols) {
+                        const double* src = out + (size_t)row * ld_out + col;
+                        if (vec_ok && col + 1 < n_cols) {
+                            const double2 v = *reinterpret_cast<const double2*>(src);
+                            prev[m][n][0] = v.x; prev[m][n][1] = v.y;
+                        } else {
+                            prev[m][n][0] = src[0];
+                            if (col + 1 < n_cols) prev[m][n][1] = src[1];
+                        }
+                    }
+                }
+        }
         int prev_stage = -1;                        // stage whose release is still owed (one k-group late, see below)
         for (int c = 0; c < n_chunks; ++c) {
             const int ng = min(KGS, kg_len - c * KGS);
@@ -227,13 +251,20 @@ gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
         const int row0 = pr * BM + wr * 32 + (lane >> 2);
         const int col0 = pc * BNT + wc * (8 * NT) + 2 * (lane & 3);
         const bool interior = vec_ok && pr * BM + BM <= n_rows && pc * BNT + BNT <= n_cols;
+        auto value = [&](int m, int n, int i) -> double {
+            if constexpr (MODE == 1) return fma(scale, acc[m][n][i], prev[m][n][i]);
+            else return scale * acc[m][n][i];
+        };
         if (interior) {
             double* base = out + (size_t)row0 * ld_out + col0;
 #pragma unroll
             for (int m = 0; m < 4; ++m)
 #pragma unroll
-                for (int n = 0; n < NT; ++n)
-                    st_cs_f64x2(base + (size_t)(m * 8) * ld_out + n * 8, scale * acc[m][n][0], scale * acc[m][n][1]);
+                for (int n = 0; n < NT; ++n) {
+                    double* dst = base + (size_t)(m * 8) * ld_out + n * 8;
+                    if constexpr (MODE == 1) *reinterpret_cast<double2*>(dst) = make_double2(value(m, n, 0), value(m, n, 1));   // read again soon: keep in L2
+                    else st_cs_f64x2(dst, value(m, n, 0), value(m, n, 1));
+                }
         } else {
 #pragma unroll
             for (int m = 0; m < 4; ++m)
@@ -242,15 +273,15 @@ gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
                     const int row = row0 + m * 8, col = col0 + n * 8;
                     if (row < n_rows && col < n_cols) {
                         double* dst = out + (size_t)row * ld_out + col;
-                        if (vec_ok && col + 1 < n_cols) st_cs_f64x2(dst, scale * acc[m][n][0], scale * acc[m][n][1]);
+                        if (vec_ok && col + 1 < n_cols) st_cs_f64x2(dst, value(m, n, 0), value(m, n, 1));
                         else {
-                            st_cs_f64(dst, scale * acc[m][n][0]);
-                            if (col + 1 < n_cols) st_cs_f64(dst + 1, scale * acc[m][n][1]);
+                            st_cs_f64(dst, value(m, n, 0));
+                            if (col + 1 < n_cols) st_cs_f64(dst + 1, value(m, n, 1));
                         }
                     }
                 }
         }
-        if constexpr (SYM) {
+        if constexpr (SYM && MODE == 0) {
             // mirror: every entry strictly above the diagonal also goes to its transposed position (8 lanes of a quad column
             // write 64 contiguous bytes)
 #pragma unroll
@@ -267,19 +298,19 @@ gram_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
     }
 }
 
-template <int NT, bool SYM>
+template <int NT, bool SYM, int MODE>
 static int launch(const double* A, const double* B, int n_rows, int n_cols, int kg_stride, int kg_len, double* out, long long ld_out,
                   double scale, int sms, cudaStream_t stream) {
     using C = Cfg<NT>;
-    auto kern = gram_kernel<NT, SYM>;
+    auto kern = gram_kernel<NT, SYM, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int tiles_r = (n_rows + BM - 1) / BM, tiles_c = (n_cols + C::BNT - 1) / C::BNT;
     const long long tiles = count_tiles<NT, SYM>(tiles_r, tiles_c);
     const int grid = (int)(tiles < sms ? tiles : sms);
     if ((tiles + grid - 1) / grid > 0x7fffffffLL) return LSK_ESIZE;
-    return (int)launch_pdl(kern, dim3(grid), dim3(NT == 4 ? THREADS_G4 : THREADS_G), (size_t)C::SMEM_BYTES, stream, A, B, n_rows, n_cols, kg_stride, kg_len,
-                           out, ld_out, scale, tiles);
+    return (int)launch_pdl(kern, dim3(grid), dim3((NT == 4 || MODE == 1) ? THREADS_G4 : THREADS_G), (size_t)C::SMEM_BYTES, stream, A, B,
+                           n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, tiles);
 }
 
 }  // namespace gram
@@ -295,11 +326,20 @@ int gram_launch(const double* A, const double* B, int n_rows, int n_cols, int kg
     int nt = (t128 >= 4ll * sms) ? 4 : 2;
     if (forced == 2 || forced == 4) nt = forced;
     if (symmetric) {
-        if (nt == 4) return gram::launch<4, true>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
-        return gram::launch<2, true>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
+        if (nt == 4) return gram::launch<4, true, 0>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
+        return gram::launch<2, true, 0>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
     }
-    if (nt == 4) return gram::launch<4, false>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
-    return gram::launch<2, false>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
+    if (nt == 4) return gram::launch<4, false, 0>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
+    return gram::launch<2, false, 0>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
+}
+
+// out += scale * A B^T in place (EPI_SYRK of lsk_pairwise_poly: the strip and trailing updates of lsk_potrf_upper / lsk_potri_upper);
+// `symmetric`: only the tiles that reach the diagonal or lie above it.  `sms` may be smaller than the device's SM count: the
+// look-ahead of the factorisation keeps a few SMs free for the panel chain that runs beside the trailing update.
+int gram_update_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_stride, int kg_len, double* out, long long ld_out,
+                       double scale, bool symmetric, int sms, cudaStream_t stream) {
+    if (symmetric) return gram::launch<2, true, 1>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
+    return gram::launch<2, false, 1>(A, B, n_rows, n_cols, kg_stride, kg_len, out, ld_out, scale, sms, stream);
 }
 
 }  // namespace lsk

@@ -50,6 +50,9 @@ int su4_tile_launch(int gen_id, const double* A, const double* B, int n_rows, in
 int gram_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_stride, int kg_len, double* out, long long ld_out,
                 double scale, bool symmetric, int sms, cudaStream_t stream);
 
+int gram_update_launch(const double* A, const double* B, int n_rows, int n_cols, int kg_stride, int kg_len, double* out, long long ld_out,
+                       double scale, bool symmetric, int sms, cudaStream_t stream);
+
 constexpr int PANEL_STAGE = KG_PER_STAGE * PANEL * 4;            // one panel, one stage: 2048 doubles = 16 KB
 constexpr int B_STAGE = PANEL_STAGE;
 // per tile variant (MT = 8-row fragments per warp): A panels per stage, ring depth, dynamic shared memory.  The 64-row
@@ -732,6 +735,12 @@ extern "C" int lsk_pairwise_poly(const void* A, const void* B, long long n_rows,
         LSK_GO_SYM(LSK_EPI_LINEAR, 1, 1, 1);
     case LSK_EPI_SYRK:
         if (p.nforms != 1 || p.nvars != 1 || p.out_layout != LSK_OUT_ROW_MAJOR) return LSK_EARG;
+        {
+            // rank-k updates run on the Gram kernel's pipeline (lsk_gram.cu, read-modify-write mode); LSK_GRAM_TILE=-1: generic kernel
+            static const bool generic_only = [] { const char* s = getenv("LSK_GRAM_TILE"); return s && atoi(s) < 0; }();
+            if (!generic_only)
+                return gram_update_launch(a, b, nr, nc, kg_total, p.group_end[0], o, ld_out, p.scale, want_sym, sms, st);
+        }
         LSK_GO_SYM(LSK_EPI_SYRK, 1, 1, 1);
     case LSK_EPI_SPARSE:
     case LSK_EPI_FEAT_SPARSE:
