@@ -36,6 +36,10 @@ constexpr int PANEL_DBL = KG * PANEL * 4;       // one 64-row panel, all k-group
 constexpr int STAGE_DBL = 3 * PANEL_DBL;        // two A panels + one B panel: the operands of one tile
 constexpr int NSTAGE = 3;                       // 3 x 67.6 KB = 203 KB: two tiles of look-ahead
 constexpr int SMEM_BYTES = NSTAGE * STAGE_DBL * 8 + 2 * NSTAGE * 8 + 64;
+// 16 consumer warps + a producer WARPGROUP (one active lane).  Twenty warps start with 96 registers each; the producer group gives
+// most of its share back and the consumers grow to 112 (`setmaxnreg`): 4 x 32 x 24 + 16 x 32 x 112 <= 640 x 96.
+constexpr int THREADS_SO5 = (CONSUMER_WARPS + 4) * 32;
+constexpr int CONS_REGS = 112, PROD_REGS = 24;
 
 // Nested Horner over a compile-time staircase: bits [4k, 4k+4) of SHAPE = coefficient pairs of row slot k (evaluation
 // order, highest power of s2 first; slot k starts at coef[16 k], highest power of s1 first), bit 48 + k = the slot's first
@@ -77,7 +81,7 @@ __device__ __forceinline__ void stair_fixed(const LskEpilogue& p, int once, cons
 }
 
 template <unsigned long long SHAPE, bool SYM>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_SO5, 1)
 stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_rows, int n_cols,
              double* __restrict__ out, long long ld_out, const __grid_constant__ LskEpilogue p)
 {
@@ -122,49 +126,33 @@ stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_r
             if (cur.c >= col_panels) { cur.c -= col_panels; ++cur.r; }
         }
     };
-    Cursor cons{(long long)blockIdx.x, 0, 0}, prod{(long long)blockIdx.x, 0, 0};
-    if (cons.t < n_tiles) { locate(cons); prod = cons; }
+    Cursor cons{(long long)blockIdx.x, 0, 0};
+    if (cons.t < n_tiles) locate(cons);
 
-    // ===================== producer duty (thread 0), folded into consumer warp 0 =====================
-    int p_stage = 0, issued_ahead = 0;          // tiles issued but not yet consumed by warp 0
-    uint32_t p_phase = 0;
-    // One non-blocking attempt to issue the next tile; LOOP-FREE (a loop under a thread-divergent branch inside the tile
-    // loop makes ptxas give up warp-uniformity, and with it the uniform-datapath coefficient loads of the epilogue).
-    auto produce_once = [&](bool wait_hw) -> bool {
-        if (prod.t >= n_tiles) return true;
-        const bool free_slot = wait_hw ? mbar_try_wait_once(&empty_bar[p_stage], p_phase ^ 1)
-                                       : mbar_test(&empty_bar[p_stage], p_phase ^ 1);
-        if (!free_slot) return false;
-        const double* srcA = A + (size_t)(2 * prod.r) * PANEL_DBL;       // operands are padded to ROW_PAD rows: both panels exist
-        const double* srcB = B + (size_t)prod.c * PANEL_DBL;
-        double* dst = sbuf + p_stage * STAGE_DBL;
-#ifdef LSK_TRACE
-        if (blockIdx.x == 0) { const long long pt = (prod.t - blockIdx.x) / gridDim.x; if (pt < LSK_TRACE_TILES) g_lsk_trace[0][pt][7] = clock64(); }
-#endif
-        mbar_expect_tx(&full_bar[p_stage], STAGE_DBL * 8);
-        bulk_g2s(dst, srcA, 2 * PANEL_DBL * 8, &full_bar[p_stage]);      // the two A panels are adjacent in HBM
-        bulk_g2s(dst + 2 * PANEL_DBL, srcB, PANEL_DBL * 8, &full_bar[p_stage]);
-        advance(prod);
-        if (++p_stage == NSTAGE) { p_stage = 0; p_phase ^= 1; }
-        ++issued_ahead;
-        return true;
-    };
-    auto produce_ahead = [&]() {
-        if (threadIdx.x == 0 && issued_ahead < NSTAGE) produce_once(false);
-    };
-    // the tile a warp is about to wait for must be in flight: warp-uniform poll loop (only thread 0 of the CTA ever polls)
-    auto produce_blocking = [&]() {
-        bool need = (threadIdx.x == 0) && (issued_ahead == 0);
-        unsigned done = 0;
-        while (!done) {
-            unsigned ok = 1;
-            if (need) {
-                ok = produce_once(true) ? 1u : 0u;
-                if (ok) need = false;
-            }
-            done = __all_sync(0xffffffffu, ok);
+    // ===================== producer: a warpgroup of its own, one active lane =====================
+    // (Round 1 folded the producer duty into thread 0 of consumer warp 0: ~50 single-thread instructions per tile during which
+    // that warp issues nothing.  Its three sub-partition mates take the pipe meanwhile, but the warp itself falls behind, the
+    // ring is released at ITS pace, and every other warp spins on the next full barrier: 55 try_wait iterations per warp and tile
+    // in the source-level profile, profiles/so5_ncu_summary_r02.json.)
+    if (warp >= CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
+        if (warp != CONSUMER_WARPS || lane != 0) return;
+        Cursor prod = cons;
+        int p_stage = 0;
+        uint32_t p_parity = 1;                       // first pass over the ring: the empty barriers pass immediately
+        for (; prod.t < n_tiles; advance(prod)) {
+            mbar_wait(&empty_bar[p_stage], p_parity);
+            const double* srcA = A + (size_t)(2 * prod.r) * PANEL_DBL;       // operands are padded to ROW_PAD rows: both panels exist
+            const double* srcB = B + (size_t)prod.c * PANEL_DBL;
+            double* dst = sbuf + p_stage * STAGE_DBL;
+            mbar_expect_tx(&full_bar[p_stage], STAGE_DBL * 8);
+            bulk_g2s(dst, srcA, 2 * PANEL_DBL * 8, &full_bar[p_stage]);      // the two A panels are adjacent in HBM
+            bulk_g2s(dst + 2 * PANEL_DBL, srcB, PANEL_DBL * 8, &full_bar[p_stage]);
+            if (++p_stage == NSTAGE) { p_stage = 0; p_parity ^= 1; }
         }
-    };
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
 
     // ===================== consumer warps: 4 (rows) x 4 (cols), warp tile 32 x 16 =====================
     const int wr = warp >> 2, wc = warp & 3;
@@ -193,8 +181,6 @@ stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_r
 #pragma unroll
                 for (int n = 0; n < 2; ++n) { acc[f][m][n][0] = 0.0; acc[f][m][n][1] = 0.0; }
 
-        produce_ahead();
-        produce_blocking();
         mbar_wait(&full_bar[stage], phase);
         LSK_STAMP(1);
         // ---- both bilinear forms on the tensor-core path, straight-line: tr g over k-groups [0, 7), <R_x, R_y> over [7, 11) ----
@@ -218,7 +204,6 @@ stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_r
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);      // hand the stage back to the producer
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-        --issued_ahead;
         LSK_STAMP(2);
 
         // ---- class polynomial on the accumulator fragments: ONE copy of the straight-line code, run for both halves of
@@ -230,7 +215,6 @@ stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_r
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             constexpr int R = 8;
-            produce_ahead();
             double s1[R], s2[R], res[R];
 #pragma unroll
             for (int e = 0; e < R; ++e) {
@@ -288,12 +272,12 @@ static int launch_shape(const double* A, const double* B, int n_rows, int n_cols
         auto kern = stair_kernel<SHAPE, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        return (int)launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)SMEM_BYTES, stream, A, B, n_rows, n_cols, out, ld_out, p);
+        return (int)launch_pdl(kern, dim3(grid), dim3(THREADS_SO5), (size_t)SMEM_BYTES, stream, A, B, n_rows, n_cols, out, ld_out, p);
     }
     auto kern = stair_kernel<SHAPE, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    return (int)launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)SMEM_BYTES, stream, A, B, n_rows, n_cols, out, ld_out, p);
+    return (int)launch_pdl(kern, dim3(grid), dim3(THREADS_SO5), (size_t)SMEM_BYTES, stream, A, B, n_rows, n_cols, out, ld_out, p);
 }
 
 }  // namespace so5
