@@ -10,7 +10,8 @@
 // (ncu, profiles/su4_ncu_summary_r01_s3.json: fp64 datapath 71 % busy, issue slots 46 %): five pipeline chunks per tile, each with
 // a claim-the-producer-duty attempt, a vote and an mbarrier round trip, a run-time variable map and predicated, layout-generic
 // stores.  Here everything that does not depend on the data is fixed at compile time, as in so5::stair_kernel:
-//   * ONE pipeline stage = the operands of a whole tile (two bulk copies of 42 KB, one mbarrier round trip per tile, 2 stages);
+//   * ONE pipeline stage = the operands of a whole tile (two bulk copies of 42 KB, one mbarrier round trip per tile, 2 stages),
+//     fed by a dedicated producer warpgroup;
 //   * the DMMA phase is straight-line code over the 21 k-groups with the form boundaries as immediates;
 //   * the variable map is two additions and a subtraction; the tape is the generated code selected by a template constant;
 //   * incremental tile cursor, unpredicated 16-byte streaming stores on interior tiles.
@@ -28,11 +29,15 @@ constexpr int STAGE_DBL = 2 * PANEL_DBL;        // one A panel + one B panel: th
 constexpr int NSTAGE = 2;                       // 2 x 86 KB = 172 KB: one tile of look-ahead
 constexpr int SMEM_BYTES = NSTAGE * STAGE_DBL * 8 + 2 * NSTAGE * 8 + 64;
 constexpr int TM = 64, TN = 64;                 // CTA tile
+// 16 consumer warps + a producer warpgroup with one active lane; registers move from the producer group to the consumers
+// (`setmaxnreg`: 4 x 32 x 24 + 16 x 32 x 112 <= 640 x 96), as in so5::stair_kernel
+constexpr int THREADS_SU4 = (CONSUMER_WARPS + 4) * 32;
+constexpr int CONS_REGS = 112, PROD_REGS = 24;
 
 __host__ __device__ constexpr int form_of(int gi) { return gi < 4 ? 0 : gi < 8 ? 1 : gi < 12 ? 2 : 3; }
 
 template <int GEN>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_SU4, 1)
 tile_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_rows, int n_cols,
             double* __restrict__ out, long long ld_out, const __grid_constant__ LskEpilogue p)
 {
@@ -61,40 +66,25 @@ tile_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
         if (cur.c >= col_tiles) { cur.c -= col_tiles; ++cur.r; }
     };
     Cursor cons{(long long)blockIdx.x, (int)(blockIdx.x / (unsigned)col_tiles), (int)(blockIdx.x % (unsigned)col_tiles)};
-    Cursor prod = cons;
 
-    // ===================== producer duty (thread 0), folded into consumer warp 0; loop-free (see lsk_pairwise_so5.cu) =====================
-    int p_stage = 0, issued_ahead = 0;          // tiles issued but not yet consumed by warp 0
-    uint32_t p_phase = 0;
-    auto produce_once = [&](bool wait_hw) -> bool {
-        if (prod.t >= n_tiles) return true;
-        const bool free_slot = wait_hw ? mbar_try_wait_once(&empty_bar[p_stage], p_phase ^ 1)
-                                       : mbar_test(&empty_bar[p_stage], p_phase ^ 1);
-        if (!free_slot) return false;
-        double* dst = sbuf + p_stage * STAGE_DBL;
-        mbar_expect_tx(&full_bar[p_stage], STAGE_DBL * 8);
-        bulk_g2s(dst, A + (size_t)prod.r * PANEL_DBL, PANEL_DBL * 8, &full_bar[p_stage]);
-        bulk_g2s(dst + PANEL_DBL, B + (size_t)prod.c * PANEL_DBL, PANEL_DBL * 8, &full_bar[p_stage]);
-        advance(prod);
-        if (++p_stage == NSTAGE) { p_stage = 0; p_phase ^= 1; }
-        ++issued_ahead;
-        return true;
-    };
-    auto produce_ahead = [&]() {
-        if (threadIdx.x == 0 && issued_ahead < NSTAGE) produce_once(false);
-    };
-    auto produce_blocking = [&]() {
-        bool need = (threadIdx.x == 0) && (issued_ahead == 0);
-        unsigned done = 0;
-        while (!done) {
-            unsigned ok = 1;
-            if (need) {
-                ok = produce_once(true) ? 1u : 0u;
-                if (ok) need = false;
-            }
-            done = __all_sync(0xffffffffu, ok);
+    // ===================== producer: a warpgroup of its own, one active lane =====================
+    if (warp >= CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
+        if (warp != CONSUMER_WARPS || lane != 0) return;
+        Cursor prod = cons;
+        int p_stage = 0;
+        uint32_t p_parity = 1;                       // first pass over the ring: the empty barriers pass immediately
+        for (; prod.t < n_tiles; advance(prod)) {
+            mbar_wait(&empty_bar[p_stage], p_parity);
+            double* dst = sbuf + p_stage * STAGE_DBL;
+            mbar_expect_tx(&full_bar[p_stage], STAGE_DBL * 8);
+            bulk_g2s(dst, A + (size_t)prod.r * PANEL_DBL, PANEL_DBL * 8, &full_bar[p_stage]);
+            bulk_g2s(dst + PANEL_DBL, B + (size_t)prod.c * PANEL_DBL, PANEL_DBL * 8, &full_bar[p_stage]);
+            if (++p_stage == NSTAGE) { p_stage = 0; p_parity ^= 1; }
         }
-    };
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
 
     // ===================== consumer warps: 4 (rows) x 4 (cols), warp tile 16 x 16 =====================
     const int wr = warp >> 2, wc = warp & 3;
@@ -115,8 +105,6 @@ tile_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
 #pragma unroll
                 for (int n = 0; n < 2; ++n) { acc[f][m][n][0] = 0.0; acc[f][m][n][1] = 0.0; }
 
-        produce_ahead();
-        produce_blocking();
         mbar_wait(&full_bar[stage], phase);
         // ---- the four bilinear forms on the tensor-core path, straight-line over the 21 k-groups ----
         {
@@ -139,8 +127,6 @@ tile_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_ro
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);      // hand the stage back to the producer
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-        --issued_ahead;
-        produce_ahead();                                    // the stage of the previous tile is free by now: start the next load
 
         // ---- class polynomial on the 8 accumulator entries of this lane ----
         constexpr int R = 8;
@@ -190,7 +176,7 @@ static int launch_gen(const double* A, const double* B, int n_rows, int n_cols, 
     auto kern = tile_kernel<GEN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    return (int)launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)SMEM_BYTES, stream, A, B, n_rows, n_cols, out, ld_out, p);
+    return (int)launch_pdl(kern, dim3(grid), dim3(THREADS_SU4), (size_t)SMEM_BYTES, stream, A, B, n_rows, n_cols, out, ld_out, p);
 }
 
 }  // namespace su4
