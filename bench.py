@@ -39,7 +39,7 @@ EIG = {
                ncu="profiles/c1_ncu_summary_r02.json"),
     "c2": dict(group="SO", n=5, order=100, size=16384, measure=dict(kind="matern", dim=10, lengthscale=1.0, nu=2.5), flop=756.0,
                name="C2: SO(5) Matern(nu=5/2) EigenbasisSumKernel, 100 irreps, fp64", kernel="lsk::so5::stair_kernel",
-               ncu="profiles/pairwise_ncu_summary_r01.json"),
+               ncu="profiles/so5_ncu_summary_r02.json"),
     "c3": dict(group="SU", n=4, order=20, size=16384, measure=dict(kind="heat", dim=15, lengthscale=1.0), flop=800.0,
                name="C3: SU(4) heat EigenbasisSumKernel, 20 irreps, complex128 characters", kernel="lsk::su4::tile_kernel",
                ncu="profiles/su4_ncu_summary_r02.json"),
@@ -279,9 +279,9 @@ def run_eigensum(ctx, tag, steps, warmup, size=None, with_e2e=True, shard_of=1):
         traffic, traffic_src = None, None
         if tag == "c2" and N == 16384 and ctx.world == 1:
             try:    # dram__bytes_read + dram__bytes_write of one launch: STATIC, from the committed ncu capture of this workload
-                with open(os.path.join(ROOT, "profiles", "pairwise_traffic_r01.json")) as fh:
+                with open(os.path.join(ROOT, "profiles", "pairwise_traffic_r02.json")) as fh:
                     traffic = json.load(fh)["traffic_bytes_per_launch"]
-                traffic_src = "static: profiles/pairwise_traffic_r01.json (ncu --set full capture of the same launch, not re-measured in this run)"
+                traffic_src = "static: profiles/pairwise_traffic_r02.json (ncu --set full capture of the same launch, not re-measured in this run)"
             except Exception:
                 pass
         res["roofline"] = {

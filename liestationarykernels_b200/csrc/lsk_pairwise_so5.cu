@@ -148,6 +148,9 @@ stair_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_r
             mbar_expect_tx(&full_bar[p_stage], STAGE_DBL * 8);
             bulk_g2s(dst, srcA, 2 * PANEL_DBL * 8, &full_bar[p_stage]);      // the two A panels are adjacent in HBM
             bulk_g2s(dst + 2 * PANEL_DBL, srcB, PANEL_DBL * 8, &full_bar[p_stage]);
+#ifdef LSK_TRACE
+            if (blockIdx.x == 0) { const long long pt = (prod.t - blockIdx.x) / gridDim.x; if (pt < LSK_TRACE_TILES) g_lsk_trace[0][pt][7] = clock64(); }
+#endif
             if (++p_stage == NSTAGE) { p_stage = 0; p_parity ^= 1; }
         }
         return;
