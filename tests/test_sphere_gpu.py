@@ -121,5 +121,4 @@ def test_properties_and_random_phase_kernel():
     assert space.rand(0) is None
     with pytest.raises(ValueError):
         Sphere(1)
-    with pytest.raises(NotImplementedError):
-        space.lb_eigenspaces[1].basis
+    assert space.lb_eigenspaces[1].basis(x[:5]).shape == (5, 3)          # degree-1 harmonics on S^2 (tests/test_basis_gpu.py)
