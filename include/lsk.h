@@ -92,6 +92,14 @@ int lsk_version(void);
 #define LSK_MAX_SNAPSHOT 7
 int lsk_snapshot_doubles(const void* const* src, int n, void* dst_host_mapped, unsigned long long seq, void* stream);
 
+/* lsk_embed_points2 (below) whose kernel also writes the snapshot (same slot format): the hyper-parameter check of a covariance call
+ * then costs no launch of its own.  Both operands must be non-empty; n_snap = 0 makes it a plain lsk_embed_points2. */
+int lsk_embed_points2_snapshot(const void* x, long long num_x, const int* part_x, void* out_x,
+                               const void* y, long long num_y, const int* part_y, void* out_y,
+                               int n, int is_complex, int nseg, const int* wedge, const int* group_begin, int kg_total,
+                               const void* const* snap_src, int n_snap, void* snap_dst_host_mapped, unsigned long long seq,
+                               void* stream);
+
 /* Text for a return code of any entry point (0 ok, < 0 LSK_E*, > 0 cudaError_t).  Stateless: the library keeps no
  * "last error"; every call reports through its return value. */
 const char* lsk_error_string(int code);

@@ -54,6 +54,12 @@ _PROTOTYPES = {
     "lsk_version": (ctypes.c_int, []),
     "lsk_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "lsk_snapshot_doubles": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p]),
+    "lsk_embed_points2_snapshot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                                  ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                                  ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_ulonglong,
+                                                  ctypes.c_void_p]),
     "lsk_embed_buffer_doubles": (ctypes.c_longlong, [ctypes.c_longlong, ctypes.c_int]),
     "lsk_embed_points": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),

@@ -13,6 +13,22 @@
 
 namespace lsk {
 
+// Snapshot of a few device scalars into host-mapped pinned memory (lsk_snapshot_doubles, lsk_embed_points2_snapshot): the Python layer
+// verifies its cached coefficient block against the live hyper-parameters without draining the stream.  No fence: a system-scope
+// fence has to reach every peer the process has mapped.  Instead every value travels with a tag, tag = bits(value) ^ key(seq), in one
+// 16-byte store; the host accepts a slot only when the pair is consistent, so a torn or reordered update is simply polled again.
+struct Snapshot { const double* src[LSK_MAX_SNAPSHOT]; int n; double* dst; unsigned long long seq; };
+
+__host__ __device__ inline unsigned long long snapshot_key(unsigned long long seq) { return seq * 0x9E3779B97F4A7C15ull + 0x7F4A7C159E3779B9ull; }
+
+__device__ __forceinline__ void snapshot_write(const Snapshot& snap, int t) {
+    if (t < snap.n) {
+        const double v = *snap.src[t];
+        const unsigned long long tag = (unsigned long long)__double_as_longlong(v) ^ snapshot_key(snap.seq);
+        asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(snap.dst + 2 * t), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+    }
+}
+
 struct EmbedSpec {
     int nseg;
     int wedge[LSK_MAX_FORMS];        // 1, 2 or 3
@@ -204,7 +220,8 @@ struct EmbedJob {
 
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
-embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ EmbedJob job1, int n, int kg_total) {
+embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ EmbedJob job1, int n, int kg_total,
+             const __grid_constant__ Snapshot snap) {
     pdl_launch_dependents();
     const EmbedJob& job = blockIdx.y ? job1 : job0;
     const double* __restrict__ x = job.x;
@@ -212,6 +229,7 @@ embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ Embe
     const long long num = job.num;
     const EmbedSpec& spec = job.spec;
     pdl_wait();                                   // x may come from the kernel launched just before (e.g. space.rand)
+    if (blockIdx.x == 0 && blockIdx.y == 0) snapshot_write(snap, threadIdx.x);
     const long long total = ((num + ROW_PAD - 1) / ROW_PAD) * (ROW_PAD / PANEL) * (long long)kg_total * (PANEL * 4);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx & 3);
@@ -293,12 +311,14 @@ embed_kernel(const __grid_constant__ EmbedJob job0, const __grid_constant__ Embe
 template <bool WITH_MATRIX>
 __global__ void __launch_bounds__(64)
 spin5_embed_kernel(const double* __restrict__ x0, long long num0, double* __restrict__ out0,
-                   const double* __restrict__ x1, long long num1, double* __restrict__ out1, int kg_total, int g0, int gm) {
+                   const double* __restrict__ x1, long long num1, double* __restrict__ out1, int kg_total, int g0, int gm,
+                   const __grid_constant__ Snapshot snap) {
     pdl_launch_dependents();
     const double* __restrict__ x = blockIdx.y ? x1 : x0;
     double* __restrict__ out = blockIdx.y ? out1 : out0;
     const long long num = blockIdx.y ? num1 : num0;
     pdl_wait();
+    if (blockIdx.x == 0 && blockIdx.y == 0) snapshot_write(snap, threadIdx.x);
     const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_padded) return;
@@ -338,13 +358,15 @@ spin5_embed_kernel(const double* __restrict__ x0, long long num0, double* __rest
 // (same association of the four terms as the generic kernel: results are bit-identical).
 __global__ void __launch_bounds__(64)
 su4_embed_kernel(const double* __restrict__ x0, long long num0, double* __restrict__ out0, int third0,
-                 const double* __restrict__ x1, long long num1, double* __restrict__ out1, int third1) {
+                 const double* __restrict__ x1, long long num1, double* __restrict__ out1, int third1,
+                 const __grid_constant__ Snapshot snap) {
     pdl_launch_dependents();
     const double* __restrict__ x = blockIdx.y ? x1 : x0;
     double* __restrict__ out = blockIdx.y ? out1 : out0;
     const long long num = blockIdx.y ? num1 : num0;
     const int third = blockIdx.y ? third1 : third0;           // 8: Re + Im (side A), 9: Re - Im (side B)
     pdl_wait();
+    if (blockIdx.x == 0 && blockIdx.y == 0) snapshot_write(snap, threadIdx.x);
     constexpr int KGT = 21;
     const long long rows_padded = ((num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -450,7 +472,7 @@ static bool is_su4_standard(const EmbedSpec& spec, int n, int is_complex, int kg
 }
 
 // embeds one or two operands (njobs) that share n, is_complex and kg_total with ONE launch where the layout allows it
-static int embed_jobs(EmbedJob* jobs, int njobs, int n, int is_complex, int kg_total, cudaStream_t st) {
+static int embed_jobs(EmbedJob* jobs, int njobs, int n, int is_complex, int kg_total, cudaStream_t st, const Snapshot& snap = Snapshot{}) {
     long long rows_max = 0, total_max = 0;
     for (int j = 0; j < njobs; ++j) {
         const long long rp = ((jobs[j].num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
@@ -466,7 +488,7 @@ static int embed_jobs(EmbedJob* jobs, int njobs, int n, int is_complex, int kg_t
     if (all_so5) {
         // the standard SO(5) layout [matrix | rotor]: one thread per point writes both segments
         cudaError_t e = launch_pdl(spin5_embed_kernel<true>, dim3((unsigned)((rows_max + 63) / 64), njobs), dim3(64), 0, st,
-                                   j0.x, j0.num, j0.out, j1.x, j1.num, j1.out, kg_total, 7, 0);
+                                   j0.x, j0.num, j0.out, j1.x, j1.num, j1.out, kg_total, 7, 0, snap);
         return (int)e;
     }
     bool all_su4 = true;
@@ -474,14 +496,14 @@ static int embed_jobs(EmbedJob* jobs, int njobs, int n, int is_complex, int kg_t
     if (all_su4) {
         // the standard SU(4) layout [Re | Im | Re +- Im | SO(6) image of Lambda^2]: one thread per point writes all 21 k-groups
         cudaError_t e = launch_pdl(su4_embed_kernel, dim3((unsigned)((rows_max + 63) / 64), njobs), dim3(64), 0, st,
-                                   j0.x, j0.num, j0.out, j0.spec.part[2], j1.x, j1.num, j1.out, j1.spec.part[2]);
+                                   j0.x, j0.num, j0.out, j0.spec.part[2], j1.x, j1.num, j1.out, j1.spec.part[2], snap);
         return (int)e;
     }
     long long blocks = (total_max + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     cudaError_t e;
-    if (is_complex) e = launch_pdl(embed_kernel<true>, dim3((unsigned)blocks, njobs), dim3(256), 0, st, j0, j1, n, kg_total);
-    else e = launch_pdl(embed_kernel<false>, dim3((unsigned)blocks, njobs), dim3(256), 0, st, j0, j1, n, kg_total);
+    if (is_complex) e = launch_pdl(embed_kernel<true>, dim3((unsigned)blocks, njobs), dim3(256), 0, st, j0, j1, n, kg_total, snap);
+    else e = launch_pdl(embed_kernel<false>, dim3((unsigned)blocks, njobs), dim3(256), 0, st, j0, j1, n, kg_total, snap);
     if (e != cudaSuccess) return (int)e;
     for (int j = 0; j < njobs; ++j)
         for (int s = 0; s < jobs[j].spec.nseg; ++s)
@@ -489,7 +511,7 @@ static int embed_jobs(EmbedJob* jobs, int njobs, int n, int is_complex, int kg_t
                 const long long rp = ((jobs[j].num + ROW_PAD - 1) / ROW_PAD) * ROW_PAD;
                 e = launch_pdl(spin5_embed_kernel<false>, dim3((unsigned)((rp + 63) / 64), 1), dim3(64), 0, st,
                                jobs[j].x, jobs[j].num, jobs[j].out, jobs[j].x, jobs[j].num, jobs[j].out,
-                               kg_total, jobs[j].spec.group_begin[s], 0);
+                               kg_total, jobs[j].spec.group_begin[s], 0, Snapshot{});
                 if (e != cudaSuccess) return (int)e;
             }
     return (int)cudaGetLastError();
@@ -529,37 +551,55 @@ extern "C" int lsk_embed_points2(const void* x, long long num_x, const int* part
 extern "C" int lsk_version(void) { return LSK_VERSION; }
 
 // Stateless: the text for a return code of any entry point (0 ok, < 0 LSK_E*, > 0 cudaError_t).
-// ---- snapshot of a few device scalars into host-mapped pinned memory ------------------------------------------------------
+// ---- snapshot of a few device scalars into host-mapped pinned memory: stand-alone launch ----------------------------------
 namespace lsk {
-struct SnapshotArgs { const double* src[LSK_MAX_SNAPSHOT]; };
-
-// No fence: a system-scope fence has to reach every peer the process has mapped (eight NVLink peers under NCCL: +25 us per call
-// measured at 8 GPUs, nothing at 1).  Instead every value travels with a tag, tag_t = bits(value_t) ^ key(seq); the host accepts a
-// slot only when the pair is consistent, so a torn or reordered update is simply polled again.
-__host__ __device__ inline unsigned long long snapshot_key(unsigned long long seq) { return seq * 0x9E3779B97F4A7C15ull + 0x7F4A7C159E3779B9ull; }
-
 __global__ void __launch_bounds__(32)
-snapshot_kernel(const __grid_constant__ SnapshotArgs a, int n, double* __restrict__ dst, unsigned long long seq) {
+snapshot_kernel(const __grid_constant__ Snapshot snap) {
     pdl_launch_dependents();
     pdl_wait();                                   // the scalars may have been written by the kernel launched just before
-    const int t = threadIdx.x;
-    if (t < n) {
-        const double v = *a.src[t];
-        const unsigned long long tag = (unsigned long long)__double_as_longlong(v) ^ snapshot_key(seq);
-        // one 16-byte store per slot: [value, tag]
-        asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(dst + 2 * t), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
-    }
+    snapshot_write(snap, threadIdx.x);
 }
 }  // namespace lsk
+
+static int make_snapshot(const void* const* src, int n, void* dst_host_mapped, unsigned long long seq, lsk::Snapshot& snap) {
+    snap = lsk::Snapshot{};
+    if (n == 0) return 0;
+    if (!src || !dst_host_mapped) return LSK_EARG;
+    if (n < 0 || n > LSK_MAX_SNAPSHOT) return LSK_ESIZE;
+    for (int i = 0; i < n; ++i) { if (!src[i]) return LSK_EARG; snap.src[i] = static_cast<const double*>(src[i]); }
+    snap.n = n; snap.dst = static_cast<double*>(dst_host_mapped); snap.seq = seq;
+    return 0;
+}
 
 extern "C" int lsk_snapshot_doubles(const void* const* src, int n, void* dst_host_mapped, unsigned long long seq, void* stream) {
     using namespace lsk;
     if (!src || !dst_host_mapped) return LSK_EARG;
-    if (n < 0 || n > LSK_MAX_SNAPSHOT) return LSK_ESIZE;
-    SnapshotArgs a = {};
-    for (int i = 0; i < n; ++i) { if (!src[i]) return LSK_EARG; a.src[i] = static_cast<const double*>(src[i]); }
-    return (int)launch_pdl(snapshot_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), a, n,
-                           static_cast<double*>(dst_host_mapped), seq);
+    Snapshot snap;
+    const int rc = make_snapshot(src, n, dst_host_mapped, seq, snap);
+    if (rc) return rc;
+    return (int)launch_pdl(snapshot_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), snap);
+}
+
+// lsk_embed_points2 with the snapshot written by the embedding kernel itself (no extra launch in front of the pair kernel)
+extern "C" int lsk_embed_points2_snapshot(const void* x, long long num_x, const int* part_x, void* out_x,
+                                          const void* y, long long num_y, const int* part_y, void* out_y,
+                                          int n, int is_complex, int nseg, const int* wedge, const int* group_begin, int kg_total,
+                                          const void* const* snap_src, int n_snap, void* snap_dst_host_mapped, unsigned long long seq,
+                                          void* stream) {
+    using namespace lsk;
+    if (!x || !y || !out_x || !out_y) return LSK_EARG;
+    if (num_x <= 0 || num_y <= 0) return LSK_ESIZE;              // the snapshot rides on a launch: both operands must be non-empty
+    EmbedJob jobs[2];
+    int rc = make_spec(num_x, n, is_complex, nseg, wedge, part_x, group_begin, kg_total, jobs[0].spec);
+    if (rc) return rc;
+    rc = make_spec(num_y, n, is_complex, nseg, wedge, part_y, group_begin, kg_total, jobs[1].spec);
+    if (rc) return rc;
+    Snapshot snap;
+    rc = make_snapshot(snap_src, n_snap, snap_dst_host_mapped, seq, snap);
+    if (rc) return rc;
+    jobs[0].x = static_cast<const double*>(x); jobs[0].num = num_x; jobs[0].out = static_cast<double*>(out_x);
+    jobs[1].x = static_cast<const double*>(y); jobs[1].num = num_y; jobs[1].out = static_cast<double*>(out_y);
+    return embed_jobs(jobs, 2, n, is_complex, kg_total, reinterpret_cast<cudaStream_t>(stream), snap);
 }
 
 extern "C" const char* lsk_error_string(int code) {

@@ -60,24 +60,40 @@ def _pair_args(plan: GroupPlan):
     return cached
 
 
-def embed_pair(plan: GroupPlan, x: torch.Tensor, y: torch.Tensor):
-    """Embeddings of both operands of `kernel(x, y)` with ONE launch (side A for x, side B for y)."""
+def embed_pair(plan: GroupPlan, x: torch.Tensor, y: torch.Tensor, snapshot=None):
+    """Embeddings of both operands of `kernel(x, y)` with ONE launch (side A for x, side B for y).  `snapshot` =
+    (pointer array, count, pinned destination, sequence number): the same launch also writes the hyper-parameter snapshot
+    (`lsk_embed_points2_snapshot`); when the one-launch path does not apply it is written by a launch of its own."""
     _lib.require_cuda()
     lib = _lib.load()
     x = _as_matrix_batch(x, plan.n, plan.is_complex)
     y = _as_matrix_batch(y, plan.n, plan.is_complex)
     if x.shape[0] == 0 or y.shape[0] == 0 or [s[0] for s in plan.segments_a] != [s[0] for s in plan.segments_b]:
+        if snapshot is not None:
+            snapshot_launch(snapshot)
         return embed(plan, x, "a"), embed(plan, y, "b")
     nseg, wedge, part_a, part_b, begin = _pair_args(plan)
     na, nb = _embed_doubles(x.shape[0], plan.kg_total), _embed_doubles(y.shape[0], plan.kg_total)
     both = torch.empty(na + nb, dtype=F64, device=x.device)          # one allocation for the two operands
     ea, eb = both[:na], both[na:]
     xr, yr = (torch.view_as_real(x), torch.view_as_real(y)) if plan.is_complex else (x, y)
-    _lib.check(lib.lsk_embed_points2(_lib.ptr(xr), x.shape[0], part_a, _lib.ptr(ea), _lib.ptr(yr), y.shape[0], part_b,
-                                     _lib.ptr(eb), plan.n, int(plan.is_complex), nseg, wedge, begin, plan.kg_total,
-                                     _lib.stream_ptr()), "lsk_embed_points2")
+    if snapshot is None:
+        _lib.check(lib.lsk_embed_points2(_lib.ptr(xr), x.shape[0], part_a, _lib.ptr(ea), _lib.ptr(yr), y.shape[0], part_b,
+                                         _lib.ptr(eb), plan.n, int(plan.is_complex), nseg, wedge, begin, plan.kg_total,
+                                         _lib.stream_ptr()), "lsk_embed_points2")
+    else:
+        arr, count, dst, seq = snapshot
+        _lib.check(lib.lsk_embed_points2_snapshot(_lib.ptr(xr), x.shape[0], part_a, _lib.ptr(ea), _lib.ptr(yr), y.shape[0], part_b,
+                                                  _lib.ptr(eb), plan.n, int(plan.is_complex), nseg, wedge, begin, plan.kg_total,
+                                                  arr, count, dst, seq, _lib.stream_ptr()), "lsk_embed_points2_snapshot")
     _lib.count_launch()
     return ea, eb
+
+
+def snapshot_launch(snapshot):
+    """stand-alone `lsk_snapshot_doubles` launch for a (pointer array, count, pinned destination, sequence number) tuple"""
+    arr, count, dst, seq = snapshot
+    _lib.check(_lib.load().lsk_snapshot_doubles(arr, count, dst, seq, _lib.stream_ptr()), "lsk_snapshot_doubles")
 
 
 def pairwise_poly(emb_a: torch.Tensor, emb_b: torch.Tensor, n_rows: int, n_cols: int, kg_total: int,

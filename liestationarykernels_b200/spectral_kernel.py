@@ -137,9 +137,12 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         else:
             ep = self._epilogue(normalize)
         if same:
+            if pending is not None:
+                ops.snapshot_launch(pending[4])
             ea = eb = ops.embed(plan, x, "a")
         else:
-            ea, eb = ops.embed_pair(plan, x, y)                    # one launch for both operands
+            # one launch for both operands; it also writes the hyper-parameter snapshot
+            ea, eb = ops.embed_pair(plan, x, y, snapshot=None if pending is None else pending[4])
         res = ops.pairwise_poly(ea, eb, x.shape[0], y.shape[0], plan.kg_total, ep, out=out, symmetric=same)
         if pending is not None and self._finish_hyper_read(pending) != self._ep_cache["key"]:
             ep = self._epilogue(normalize)
@@ -203,9 +206,11 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         return (normalize, self.form) + tuple(vals + host)
 
     def _enqueue_hyper_read(self, normalize):
-        """Asynchronous version of `_hyper_values`: one 32-thread kernel (`lsk_snapshot_doubles`) copies the device scalars into
-        host-mapped pinned memory and then bumps a sequence word; no copy engine, no event.  (torch.cat + a pinned copy + an event
-        put two extra launches and a DMA in front of the embedding kernel: +24 us per step at 8 GPUs, where a step is 0.31 ms.)"""
+        """Asynchronous version of `_hyper_values`: the device scalars are copied into host-mapped pinned memory by the embedding
+        launch of this call (`lsk_embed_points2_snapshot`; a 32-thread launch of its own, `lsk_snapshot_doubles`, where there is
+        no two-operand embedding), each with a tag the host polls; no copy engine, no event.  (torch.cat + a pinned copy + an event
+        put two extra launches and a DMA in front of the embedding kernel: +24 us per step at 8 GPUs, where a step is 0.31 ms.)
+        Returns the pending-read record; its last field is what the launch needs."""
         m = self.measure
         ptrs, host = [], []
         for t in (m.lengthscale, m.variance, getattr(m, "nu", None), self.normalizer if normalize else None):
@@ -220,15 +225,13 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
             self._pinned_np = self._pinned.numpy().view("uint64")
             self._seq = 0
         self._seq += 1
-        lib = _lib.load()
         arr = (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
-        _lib.check(lib.lsk_snapshot_doubles(arr, len(ptrs), ctypes.c_void_p(self._pinned.data_ptr()), self._seq, _lib.stream_ptr()),
-                   "lsk_snapshot_doubles")
-        return (len(ptrs), host, normalize, self._seq)
+        launch = (arr, len(ptrs), ctypes.c_void_p(self._pinned.data_ptr()), self._seq)     # handed to the embedding launch
+        return (len(ptrs), host, normalize, self._seq, launch)
 
     def _finish_hyper_read(self, pending):
         """Poll the pinned slots until every [value, tag] pair is consistent for this call's sequence number (see lsk.h)."""
-        n, host, normalize, seq = pending
+        n, host, normalize, seq, _ = pending
         words = self._pinned_np
         key = (seq * 0x9E3779B97F4A7C15 + 0x7F4A7C159E3779B9) & 0xFFFFFFFFFFFFFFFF
         # Spin (the wait is at most one call of GPU work), then sleep in short slices if the queue ahead of this call is long.
