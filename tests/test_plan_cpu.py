@@ -140,8 +140,8 @@ def test_lazy_results_become_real_gpytorch_objects_when_gpytorch_is_importable(m
     torch.manual_seed(0)
     a, b = torch.randn(70, 24, dtype=torch.float64), torch.randn(33, 24, dtype=torch.float64)
     gram = lazy.LazyGram(ops.PanelMatrix.from_dense(a), ops.PanelMatrix.from_dense(b), 0.25)
-    monkeypatch.setitem(sys.modules, "gpytorch", None)
-    monkeypatch.setitem(sys.modules, "linear_operator", None)
+    for name in ("gpytorch", "gpytorch.lazy", "linear_operator", "linear_operator.operators"):
+        monkeypatch.setitem(sys.modules, name, None)       # (oracle/ref_shim.py may have registered its own stand-ins in this process)
     assert lazy.as_reference_lazy(gram) is gram                       # nothing importable: the stand-in object
     mod, sub = types.ModuleType("gpytorch"), types.ModuleType("gpytorch.lazy")
     sub.NonLazyTensor, sub.MatmulLazyTensor = NonLazyTensor, MatmulLazyTensor
