@@ -578,15 +578,17 @@ struct RotPair {
         for (int a = 0; a < 5; ++a)
 #pragma unroll
             for (int b = 0; b < 5; ++b) M[a][b] = 0.0;
+        const double* __restrict__ ga = swap ? gj : gi;       // swap: M = lift_j^T lift_i - the same code on exchanged pointers
+        const double* __restrict__ gb = swap ? gi : gj;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            double xr[5], yr[5];
+            double ar[5], br[5];
 #pragma unroll
-            for (int a = 0; a < 5; ++a) { xr[a] = gi[c * 5 + a]; yr[a] = gj[c * 5 + a]; }
+            for (int a = 0; a < 5; ++a) { ar[a] = ga[c * 5 + a]; br[a] = gb[c * 5 + a]; }
 #pragma unroll
             for (int a = 0; a < 5; ++a)
 #pragma unroll
-                for (int b = 0; b < 5; ++b) M[a][b] = swap ? fma(yr[a], xr[b], M[a][b]) : fma(xr[a], yr[b], M[a][b]);
+                for (int b = 0; b < 5; ++b) M[a][b] = fma(ar[a], br[b], M[a][b]);
         }
         Consts k;
         double trT = 0.0, trT2 = 0.0;
@@ -638,6 +640,7 @@ struct RotPair {
 };
 
 constexpr int ROT_CHUNK = 128;          // subgroup samples staged per pass (4 doubles each)
+constexpr int ROT_COLS_PER_CTA = 32;    // MODE 0: columns per CTA (8 groups of 4)
 
 template <unsigned long long SHAPE, int MODE>
 __global__ void __launch_bounds__(256, 3)
@@ -658,10 +661,13 @@ homog5_rot_kernel(const double* __restrict__ gx, const double* __restrict__ gy, 
 #pragma unroll
         for (int c = 0; c < 3; ++c) aff[v][c] = p.aff[v][c];
     const double inv_avg = p.scale / (double)n_avg;
-    const int j_begin = MODE == 0 ? blockIdx.x * 4 + threadIdx.x : threadIdx.x;
-    const int j_step = MODE == 0 ? n_cols : 32;             // MODE 0: a single column per thread
+    // MODE 0: ROT_COLS_PER_CTA / 4 column groups per CTA (the subgroup samples are staged once per CTA, and a CTA lives long enough
+    // for its launch and drain to disappear); MODE 1: all columns, 32 at a time
+    const int j_begin = MODE == 0 ? blockIdx.x * ROT_COLS_PER_CTA + threadIdx.x : threadIdx.x;
+    const int j_step = MODE == 0 ? 4 : 32;
+    const int j_end = MODE == 0 ? min(blockIdx.x * ROT_COLS_PER_CTA + ROT_COLS_PER_CTA, ((n_cols + 3) / 4) * 4) : ((n_cols + 31) / 32) * 32;
     double fsum = 0.0;
-    for (int j0 = j_begin; j0 < (MODE == 0 ? j_begin + 1 : ((n_cols + 31) / 32) * 32); j0 += j_step) {
+    for (int j0 = j_begin; j0 < j_end; j0 += j_step) {
         const int j = j0;
         const bool active = (i < n_rows) && (j < n_cols);
         typename RP::Consts k = {};
@@ -671,7 +677,7 @@ homog5_rot_kernel(const double* __restrict__ gx, const double* __restrict__ gy, 
         for (int m = 0; m < TOTAL; ++m) S[m] = 0.0;
         for (int k0 = 0; k0 < n_avg; k0 += ROT_CHUNK) {
             const int kc = min(ROT_CHUNK, n_avg - k0);
-            if (MODE == 0 || n_avg > ROT_CHUNK || j0 == j_begin) {      // MODE 1 with few samples: staged once per CTA
+            if (n_avg > ROT_CHUNK || j0 == j_begin) {                   // few samples: staged once per CTA
                 __syncthreads();
                 for (int q = tid; q < kc; q += 256) {
                     const double c = h[(size_t)(k0 + q) * 25 + 18], s = h[(size_t)(k0 + q) * 25 + 19];   // R[0][0], R[0][1]
@@ -684,7 +690,7 @@ homog5_rot_kernel(const double* __restrict__ gx, const double* __restrict__ gy, 
         }
         // dense coefficient table: irrep l, monomial m -> coef[l * TOTAL + m]
         if (MODE == 0) {
-            if (!active) return;
+            if (active)
             for (int l = 0; l < p.nterms; ++l) {
                 double v = 0.0;
 #pragma unroll
@@ -810,7 +816,7 @@ extern "C" int lsk_homog_pairs(const void* lifted_x, const void* lifted_y, const
         if (mtop == 11) {
             // t = 3 and every R is a plane rotation [[c, s], [-s, c]]: trigonometric-polynomial kernel
             LskEpilogue q;
-            dim3 rblock(4, 64), rgrid((unsigned)((n_cols + 3) / 4), (unsigned)((n_rows + 63) / 64));
+            dim3 rblock(4, 64), rgrid((unsigned)((n_cols + ROT_COLS_PER_CTA - 1) / ROT_COLS_PER_CTA), (unsigned)((n_rows + 63) / 64));
             if (rgrid.y <= 65535u) {
                 if (covered(SH10) && densify_rows<SH10>(p, q)) {
                     homog5_rot_kernel<SH10, 0><<<rgrid, rblock, 0, st>>>(gx, gy, hh, (int)n_rows, (int)n_cols, n_avg, o, ld_out, nullptr, q);
