@@ -125,9 +125,12 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         same = y is x and plan.segments_a == plan.segments_b      # one embedding serves both sides
         cached = self._ep_cache.get("ep") if self._ep_cache.get("flags") == (normalize, self.form) else None
         pending = None
-        if cached is not None and not self.assume_static:
+        capturing = cached is not None and torch.cuda.is_current_stream_capturing()
+        if cached is not None and not self.assume_static and not capturing:
             pending = self._enqueue_hyper_read(normalize)
-        if pending is not None:
+        if capturing:
+            ep = cached               # inside a CUDA-graph capture the host cannot wait for the device: the captured launch keeps the block
+        elif pending is not None:
             # Optimistic launch: start the stream-ordered read of the hyper-parameters, launch with the cached coefficient
             # block, and only then wait for the read.  The read completes when the work queued BEFORE this call has finished, so
             # the host stays one call ahead of the GPU instead of draining it on every call (a blocking read cost 90 us of idle

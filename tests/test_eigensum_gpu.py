@@ -227,3 +227,30 @@ def test_eval_mode_follows_hyperparameter_writes(how):
     assert not torch.equal(k1, k2)
     assert torch.equal(k2, k3)
     assert torch.allclose(k4, 2.5 * k2, rtol=1e-14, atol=0)
+
+
+def test_forward_can_be_captured_in_a_cuda_graph():
+    """Inside a stream capture the host cannot poll the hyper-parameter snapshot, so the call launches with the cached
+    coefficient block and does no device->host read; the replayed graph reproduces the eager result bit for bit."""
+    from liestationarykernels_b200.spaces import SO
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(5)
+    space = SO(3, order=20)
+    kern = EigenbasisSumKernel(MaternSpectralMeasure(space.dim, 0.7, 2.5), space).eval()
+    x, y = space.rand(300), space.rand(200)
+    out = torch.empty(300, 200, dtype=torch.float64, device="cuda")
+    with torch.no_grad():
+        eager = kern(x, y).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            kern(x, y, out=out)              # warm the allocator on the capture stream
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            kern(x, y, out=out)
+        out.zero_()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
