@@ -281,6 +281,66 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         """Drop the cached coefficient block (only needed with `assume_static = True`)."""
         self._ep_cache = {}
 
+    # ---- host-buffer entry: covariance written into host memory ------------------------------------------------
+    HOST_ROW_BLOCK = 2048        # rows per device block of `evaluate_to_host` (a multiple of 128)
+
+    def evaluate_to_host(self, x, y=None, out=None, normalize=True, row_block=None):
+        """kernel(x, y) with HOST buffers on both sides: `x`, `y` may be host tensors (pinned for asynchronous copies), the
+        result is written into `out`, a float64 [N, M] host tensor (allocated pinned when None) and returned once complete.
+        The N x M covariance never exists on the device: the operands are embedded once, row blocks of `row_block` rows are
+        computed into two alternating device buffers, and each block's device->host copy runs on a second stream while the
+        next block is computed, so the call costs the PCIe time of the result plus one block of compute (at C2, 16384^2:
+        the 2.1 GB copy dominates 2.4 ms of compute).  Values are those of `forward` bit for bit (same tiles, same
+        coefficient block)."""
+        manifold = self.manifold
+        dev = manifold._lambdas.device
+        xd = x.to(dev, non_blocking=True)
+        yd = xd if y is None or y is x else y.to(dev, non_blocking=True)
+        N, M = xd.shape[0], yd.shape[0]
+        if out is None:
+            out = torch.empty((N, M), dtype=torch.float64).pin_memory()
+        elif out.is_cuda or out.dtype != torch.float64 or tuple(out.shape) != (N, M) or (M and out.stride(1) != 1):
+            raise ValueError("out must be a float64 [%d, %d] host tensor with unit column stride" % (N, M))
+        rb = int(row_block or self.HOST_ROW_BLOCK)
+        if rb <= 0 or rb % 128:
+            raise ValueError("row_block must be a positive multiple of 128")
+        with torch.no_grad():
+            if self.training and normalize:
+                self.compute_normalizer()
+            if not isinstance(manifold, CompactLieGroup) or N <= rb or M == 0:
+                if N and M:
+                    out.copy_(self.forward(xd, yd, normalize=normalize))
+                return out
+            plan = manifold.plan
+            ep = self._epilogue(normalize)
+            ea, eb = ops.embed_pair(plan, xd, yd)
+            main = torch.cuda.current_stream(dev)
+            side = getattr(self, "_copy_stream", None)
+            if side is None or side.device != main.device:
+                side = self._copy_stream = torch.cuda.Stream(dev)
+            bufs = [torch.empty((rb, M), dtype=torch.float64, device=dev) for _ in range(2)]
+            for b in bufs:
+                b.record_stream(side)
+            drained = [None, None]
+            for i, r0 in enumerate(range(0, N, rb)):
+                rows = min(rb, N - r0)
+                if drained[i % 2] is not None:
+                    main.wait_event(drained[i % 2])                  # the block's buffer is free once its last copy has left
+                block = bufs[i % 2][:rows]
+                ops.pairwise_poly(ea[(r0 // 64) * plan.kg_total * 256:], eb, rows, M, plan.kg_total, ep, out=block)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    out[r0:r0 + rows].copy_(block, non_blocking=True)
+                    drained[i % 2] = torch.cuda.Event()
+                    drained[i % 2].record(side)
+            main.wait_stream(side)                                   # stream order: work queued after this call sees the copies done
+            if not out.is_pinned():
+                return out                                           # pageable destination: the copies above were synchronous
+            side.synchronize()
+        return out
+
 
 class EigenbasisKernel(AbstractSpectralKernel):
     """k(x, y) = sum_l a(lambda_l) sum_k f_{l,k}(x) conj(f_{l,k}(y)) over an explicit orthonormal basis of every eigenspace

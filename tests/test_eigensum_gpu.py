@@ -254,3 +254,29 @@ def test_forward_can_be_captured_in_a_cuda_graph():
         graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+@pytest.mark.parametrize("group,n,order,nx,ny,rb,pinned", [("SO", 5, 20, 700, 333, 256, True), ("SO", 5, 20, 515, 260, 128, False),
+                                                           ("SU", 4, 10, 641, 200, 256, True), ("SO", 3, 20, 100, 90, 2048, True)])
+def test_evaluate_to_host_equals_forward(group, n, order, nx, ny, rb, pinned):
+    """Host-buffer entry: row blocks computed into alternating device buffers and copied out on a second stream give the
+    same bits as one `forward` call followed by a copy (also with a ragged last block and a pageable destination)."""
+    from liestationarykernels_b200.spectral_kernel import EigenbasisSumKernel
+    from liestationarykernels_b200.spectral_measure import MaternSpectralMeasure
+    torch.manual_seed(11)
+    space = _space(group, n, order)
+    kern = EigenbasisSumKernel(MaternSpectralMeasure(space.dim, 0.9, 1.5, 2.0), space).eval()
+    x, y = space.rand(nx), space.rand(ny)
+    with torch.no_grad():
+        want = kern(x, y).cpu()
+    xh, yh = x.cpu(), y.cpu()
+    out = torch.full((nx, ny), float("nan"), dtype=torch.float64)
+    if pinned:
+        xh, yh, out = xh.pin_memory(), yh.pin_memory(), out.pin_memory()
+    got = kern.evaluate_to_host(xh, yh, out=out, row_block=rb)
+    assert got is out
+    assert torch.equal(got, want)
+    again = kern.evaluate_to_host(x, y, row_block=rb)           # device inputs, destination allocated by the call
+    assert again.is_pinned() and torch.equal(again, want)
+    with pytest.raises(ValueError):
+        kern.evaluate_to_host(xh, yh, out=out, row_block=100)
