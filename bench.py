@@ -119,9 +119,33 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local)
+        self.numa = self._bind_to_gpu_numa_node() if self.world > 1 else None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         self._flush = None
+
+    def _bind_to_gpu_numa_node(self):
+        """Multi-rank runs: keep this rank's threads (and, by first touch, its pinned host buffers) on the NUMA node its GPU
+        hangs off, so that the end-to-end copies do not cross the socket interconnect.  Best effort: returns the node or None."""
+        try:
+            prop = self.torch.cuda.get_device_properties(self.local)
+            path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+            with open(path) as fh:
+                node = int(fh.read().strip())
+            if node < 0:
+                return None
+            with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+                cpus = set()
+                for part in fh.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if not allowed:
+                return None
+            os.sched_setaffinity(0, allowed)
+            return node
+        except Exception:
+            return None
 
     def barrier(self):
         if self.world > 1:
@@ -692,6 +716,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": res.pop("config"), "roofline": res.pop("roofline"),
                 "e2e": res.pop("e2e"), "gpu_launches": res.pop("launches"), "clocks": clocks}
         line.update(res)
+        if ctx.world > 1:
+            line["host_affinity"] = {"rank0_numa_node": ctx.numa, "note": "each rank pinned to the CPUs of its GPU's NUMA node (best effort; null = not available)"}
         if ctx.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(tag)
             if tag in EIG:
