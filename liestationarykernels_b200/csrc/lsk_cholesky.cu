@@ -17,6 +17,8 @@
 //     lsk_trsm_lower   the forward solve for a block of right-hand sides (trsm_kernel + repack_kernel + tile kernel)
 //     lsk_potri_upper  Y = U^{-T} by the same sweep on the identity and A^{-1} = sum_k Y_k^T Y_k on the triangular tile
 //                      schedule: 2 n^3 / 3 flop, the zero structure of U^{-T} used exactly at block level
+#include <cstdlib>
+
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
 
@@ -165,6 +167,302 @@ diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __res
 #pragma unroll
         for (int k = 0; k < 8; ++k) Wg[wg_index(tr + 16 * i, tc + 16 * k)] = a[i][k];
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// diagonal block, tiled: the same results (U_kk and B = U_kk^{-T}) with the dependent chain cut to what it has to be.
+//
+// The sweep above pays a CTA-wide barrier, a shared-memory round trip and a reciprocal on the dependent path of each of
+// its 2 x 128 steps (~190 ns per step).  Here the block is cut into 16 x 16 tiles (only the 36 on or above the diagonal are
+// kept, each in shared memory with row stride 18), and per tile row jb:
+//   S1  one warp eliminates the 16 x 16 diagonal tile in registers: lane c < 16 owns column c of the (symmetric) tile, lane
+//       16 + c owns column c of an identity that receives the same row operations.  The pivot row reaches the lanes by warp
+//       shuffles from lane j (its column IS the pivot row); the update is  v_r -= (D_rj D_jc) / d_j  with the product formed
+//       before 1 / d_j is known, so a step's dependent path is shuffle -> reciprocal -> one fused multiply-add and there is
+//       no barrier inside the 16 steps.  Out come U_jj = diag(d^-1/2) R and, from the identity side, its inverse transpose
+//       B_jj = diag(d^-1/2) L_unit^{-1} - no separate inversion of the diagonal tiles.
+//   S2  the tile row right of it, U_j,: = B_jj A_j,: - one 16 x 16 x 16 product per warp on the fp64 tensor-core path,
+//   S3a the next tile row receives its rank-16 update (so that S1 of the next tile can start),
+//   S3b the rest of the trailing tiles are updated by warps 1-7 WHILE warp 0 runs S1 of the next tile (look-ahead).
+//   The off-diagonal tiles of B follow by recursive doubling, B_21 = -B_22 L_21 B_11 at tile sizes 16, 32, 64: products of
+//   16 x 16 tiles spread over the eight warps, six barriers in all.
+// Every tile product is DMMA.8x8x4: with plain DFMA a 2 x 4 register block per lane needs three 16-byte shared-memory loads
+// per eight multiply-adds and the ONE shared-memory pipe of the SM (not the fp64 pipe) sets the pace - measured 1 480 cycles
+// per tile product; the DMMA fragments need four 8-byte loads per 1 024 multiply-adds.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TS = 18;                           // row stride of a 16 x 16 tile in shared memory (doubles)
+constexpr int TILE = 16 * TS;
+constexpr int NTL = NB / 16;                     // tiles per side
+constexpr int TRI = NTL * (NTL + 1) / 2;         // tiles in a triangle
+constexpr int DIAGT_SMEM = ((2 * TRI + 16) * TILE + NB + 64) * 8;
+
+__device__ __forceinline__ int ut(int bi, int bj) { return bj * (bj + 1) / 2 + bi; }     // upper tile (bi <= bj)
+__device__ __forceinline__ int lt(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // lower tile (bi >= bj)
+
+// 1 / sqrt(x) for normal positive x: hardware seed + a cubic and a linear Newton step
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    y = fma(y * e, fma(0.375, e, 0.5), y);
+    const double e2 = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e2, y);
+}
+
+// Store under a lane-dependent condition as ONE predicated instruction.  Written as `if (p) *ptr = v` the compiler emitted a
+// divergent branch per store, and sixteen of those in a row cost the lone warp of step S1 5 900 cycles (tools/s1_micro.cu).
+__device__ __forceinline__ void st_global_if(double* ptr, double v, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f64 [%0], %1; }" :: "l"(ptr), "d"(v), "r"((int)p) : "memory");
+}
+
+// Accumulator of a 16 x 16 tile held by one warp as 2 x 2 DMMA fragments: acc[a][b][e] = C[8 a + g][8 b + 2 tig + e],
+// g = lane / 4, tig = lane % 4.
+struct TileAcc {
+    double c[2][2][2];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+    }
+    __device__ __forceinline__ void load(const double* __restrict__ C, int g, int tig) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const double2 v = *reinterpret_cast<const double2*>(C + (8 * a + g) * TS + 8 * b + 2 * tig);
+                c[a][b][0] = v.x; c[a][b][1] = v.y;
+            }
+    }
+    __device__ __forceinline__ void store(double* __restrict__ C, int g, int tig) const {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+                *reinterpret_cast<double2*>(C + (8 * a + g) * TS + 8 * b + 2 * tig) = make_double2(c[a][b][0], c[a][b][1]);
+    }
+    // C (+/-)= P^T Q:  C[i][j] += sum_k P[k][i] Q[k][j]
+    template <bool NEG>
+    __device__ __forceinline__ void mma_tn(const double* __restrict__ P, const double* __restrict__ Q, int g, int tig) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+            double a0 = P[(k + tig) * TS + g], a1 = P[(k + tig) * TS + 8 + g];
+            const double b0 = Q[(k + tig) * TS + g], b1 = Q[(k + tig) * TS + 8 + g];
+            if (NEG) { a0 = -a0; a1 = -a1; }
+            dmma884(c[0][0], a0, b0); dmma884(c[0][1], a0, b1);
+            dmma884(c[1][0], a1, b0); dmma884(c[1][1], a1, b1);
+        }
+    }
+    // C (+/-)= P Q:  C[i][j] += sum_k P[i][k] Q[k][j]
+    template <bool NEG>
+    __device__ __forceinline__ void mma_nn(const double* __restrict__ P, const double* __restrict__ Q, int g, int tig) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+            double a0 = P[g * TS + k + tig], a1 = P[(8 + g) * TS + k + tig];
+            const double b0 = Q[(k + tig) * TS + g], b1 = Q[(k + tig) * TS + 8 + g];
+            if (NEG) { a0 = -a0; a1 = -a1; }
+            dmma884(c[0][0], a0, b0); dmma884(c[0][1], a0, b1);
+            dmma884(c[1][0], a1, b0); dmma884(c[1][1], a1, b1);
+        }
+    }
+};
+
+#ifdef LSK_TRACE
+__device__ long long g_diag_trace[8][80];
+#define DIAG_STAMP(ev) do { long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); if (lane == 0) g_diag_trace[warp][ev] = c_; } while (0)
+#else
+#define DIAG_STAMP(ev) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+diag_tile_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __restrict__ Wg, int* __restrict__ info)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Up = reinterpret_cast<double*>(smem_raw);         // 36 upper tiles: A_kk, then U_kk
+    double* Bp = Up + TRI * TILE;                             // 36 lower tiles: B = U_kk^{-T}
+    double* Tt = Bp + TRI * TILE;                             // 16 scratch tiles of the doubling steps
+    double* rsv = Tt + 16 * TILE;                             // 1 / U_jj
+    double* piv = rsv + NB;                                   // 2 x 32: the pivot row of S1, double-buffered
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int g = lane >> 2, tig = lane & 3;                  // DMMA fragment coordinates
+    DIAG_STAMP(0);
+
+    // ---- load the upper tiles (diagonal tiles mirrored: S1 works on the full symmetric tile); identity padding when ragged
+    {
+        const int r = t >> 4, c = t & 15;
+        double tmp[TRI];                                      // all 36 loads in flight before the first store
+#pragma unroll
+        for (int bj = 0; bj < NTL; ++bj)
+#pragma unroll
+            for (int bi = 0; bi <= bj; ++bi) {
+                int R = 16 * bi + r, C = 16 * bj + c;
+                if (bi == bj && c < r) { const int x = R; R = C; C = x; }
+                const bool in = R < nb && C < nb;                 // ragged block: read a valid entry, then select
+                const double x = A[(size_t)(k0 + (in ? R : 0)) * lda + k0 + (in ? C : 0)];
+                tmp[bj * (bj + 1) / 2 + bi] = in ? x : ((R == C) ? 1.0 : 0.0);
+            }
+#pragma unroll
+        for (int i = 0; i < TRI; ++i) Up[i * TILE + r * TS + c] = tmp[i];
+    }
+    __syncthreads();
+    DIAG_STAMP(1);
+
+#pragma unroll 1
+    for (int jb = 0; jb < NTL; ++jb) {
+        const int o = 16 * jb;
+        if (warp == 0) {
+            // ---- S1: diagonal tile (lanes 0-15) and the identity that receives the same row operations (lanes 16-31).
+            // Nothing in here branches on the lane: 1 450 cycles for the 16 steps (tools/s1_micro.cu).
+            double* Dt = Up + ut(jb, jb) * TILE;
+            const int c = lane & 15;
+            const bool iside = lane >= 16;
+            double v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const double x = Dt[r * TS + c];
+                v[r] = iside ? ((r == c) ? 1.0 : 0.0) : x;
+            }
+            double dc = 1.0;
+            int bad = -1;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // the pivot row D[j][:] is spread over the lanes (lane c holds D[j][c] in v[j]): all-gather through shared memory
+                double* pb = piv + (j & 1) * 32;
+                pb[lane] = v[j];                                  // identity side: scratch slots 16 .. 31
+                __syncwarp();
+                double row[16];
+#pragma unroll
+                for (int r = (j & ~1); r < 16; r += 2) {
+                    const double2 x = *reinterpret_cast<const double2*>(pb + r);
+                    row[r] = x.x; row[r + 1] = x.y;
+                }
+                const double d = row[j];
+                const double id = fast_rcp(d);
+                dc = (c == j) ? d : dc;
+                bad = (bad < 0 && !(d > 0.0) && o + j < nb) ? j : bad;
+#pragma unroll
+                for (int r = j + 1; r < 16; ++r) v[r] = fma(-(row[r] * v[j]), id, v[r]);
+            }
+            if (bad >= 0) {                                       // warp-uniform: not positive definite (LAPACK info convention)
+                if (lane == 0) atomicCAS(info, 0, k0 + o + bad + 1);
+            }
+            rsv[o + c] = fast_rsqrt(dc);                          // both halves hold the same pivots
+            __syncwarp();
+            // rows scaled by d_r^-1/2: U[r][c] (kept for c >= r) / B[r][c] (zero for c > r by itself).  Global copies: U into A,
+            // B into the W block (whose zeros come from the memset of the workspace).
+            double* dst = Up + (iside ? (TRI + lt(jb, jb)) * TILE : ut(jb, jb) * TILE) + c;
+            double* gdst = iside ? Wg + wg_index(o, o + c) : A + (size_t)(k0 + o) * lda + k0 + o + c;
+            const long long gstep = iside ? 4 : lda;
+            const bool col_ok = iside || o + c < nb;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const double u = v[r] * rsv[o + r];
+                dst[r * TS] = (iside || r <= c) ? u : 0.0;
+                st_global_if(gdst + r * gstep, u, col_ok && (iside ? (r >= c) : (r <= c)));
+            }
+        } else if (jb > 0) {
+            // ---- S3b of the previous tile row: trailing tiles below the row that S3a already served
+            const int rows = NTL - 1 - jb, tiles = rows * (rows + 1) / 2;
+            for (int idx = warp - 1; idx < tiles; idx += 7) {
+                int rem = idx, bi = jb + 1, len = rows;
+                while (rem >= len) { rem -= len; ++bi; --len; }
+                const int bj = bi + rem;
+                TileAcc acc;
+                double* Ct = Up + ut(bi, bj) * TILE;
+                acc.load(Ct, g, tig);
+                acc.mma_tn<true>(Up + ut(jb - 1, bi) * TILE, Up + ut(jb - 1, bj) * TILE, g, tig);
+                acc.store(Ct, g, tig);
+            }
+        }
+        DIAG_STAMP(2 + 6 * jb);
+        __syncthreads();
+        DIAG_STAMP(3 + 6 * jb);
+        // ---- S2: tile row jb right of the diagonal, U_j,bj = B_jj A_j,bj (in place)
+        if (warp < NTL - 1 - jb) {
+            double* Xt = Up + ut(jb, jb + 1 + warp) * TILE;
+            TileAcc acc;
+            acc.zero();
+            acc.mma_nn<false>(Bp + lt(jb, jb) * TILE, Xt, g, tig);
+            __syncwarp();
+            acc.store(Xt, g, tig);
+            const int C0 = 16 * (jb + 1 + warp) + 2 * tig;   // the factor goes back to A as it is produced (columns < nb: rows are then < nb too)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    double* gp = A + (size_t)(k0 + o + 8 * a + g) * lda + k0 + C0 + 8 * b;
+                    st_global_if(gp, acc.c[a][b][0], C0 + 8 * b < nb);
+                    st_global_if(gp + 1, acc.c[a][b][1], C0 + 8 * b + 1 < nb);
+                }
+        }
+        DIAG_STAMP(4 + 6 * jb);
+        __syncthreads();
+        DIAG_STAMP(5 + 6 * jb);
+        // ---- S3a: rank-16 update of the next tile row
+        if (warp < NTL - 1 - jb) {
+            const int bi = jb + 1, bj = jb + 1 + warp;
+            TileAcc acc;
+            double* Ct = Up + ut(bi, bj) * TILE;
+            acc.load(Ct, g, tig);
+            acc.mma_tn<true>(Up + ut(jb, bi) * TILE, Up + ut(jb, bj) * TILE, g, tig);
+            acc.store(Ct, g, tig);
+        }
+        DIAG_STAMP(6 + 6 * jb);
+        __syncthreads();
+        DIAG_STAMP(7 + 6 * jb);
+    }
+
+    DIAG_STAMP(50);
+
+    // ---- B = U^{-T} by recursive doubling:  [B11 0; B21 B22],  B21 = -B22 L21 B11,  L21 = (U12)^T
+#pragma unroll 1
+    for (int hh = 1; hh <= 4; hh *= 2) {
+        const int per_merge = hh * hh;
+        // T[k1][bj] = sum_{k2 >= bj} L(p + h + k1, p + k2) B(p + k2, p + bj)
+        for (int slot = 0; slot < (hh == 4 ? 2 : 1); ++slot) {
+            int q, k1, bj;
+            if (hh == 1) { q = warp; k1 = 0; bj = 0; if (warp >= 4) continue; }
+            else if (hh == 2) { q = warp >> 2; k1 = (warp >> 1) & 1; bj = warp & 1; }
+            else { q = 0; k1 = slot ? 2 + (warp >> 2) : (warp >> 2); bj = slot ? 3 - (warp & 3) : (warp & 3); }
+            const int p = 2 * hh * q;
+            TileAcc acc;
+            acc.zero();
+            for (int k2 = bj; k2 < hh; ++k2)
+                acc.mma_tn<false>(Up + ut(p + k2, p + hh + k1) * TILE, Bp + lt(p + k2, p + bj) * TILE, g, tig);
+            acc.store(Tt + (q * per_merge + k1 * hh + bj) * TILE, g, tig);
+        }
+        __syncthreads();
+        // B(p + h + bi, p + bj) = - sum_{k1 <= bi} B(p + h + bi, p + h + k1) T[k1][bj]
+        for (int slot = 0; slot < (hh == 4 ? 2 : 1); ++slot) {
+            int q, bi, bj;
+            if (hh == 1) { q = warp; bi = 0; bj = 0; if (warp >= 4) continue; }
+            else if (hh == 2) { q = warp >> 2; bi = (warp >> 1) & 1; bj = warp & 1; }
+            else { q = 0; bi = slot ? 3 - (warp & 3) : (warp & 3); bj = slot ? 2 + (warp >> 2) : (warp >> 2); }
+            const int p = 2 * hh * q;
+            TileAcc acc;
+            acc.zero();
+            for (int k1 = 0; k1 <= bi; ++k1)
+                acc.mma_nn<true>(Bp + lt(p + hh + bi, p + hh + k1) * TILE, Tt + (q * per_merge + k1 * hh + bj) * TILE, g, tig);
+            acc.store(Bp + lt(p + hh + bi, p + bj) * TILE, g, tig);
+            const int kk0 = 16 * (p + hh + bi) + g, q0 = 16 * (p + bj) + 2 * tig;      // and into the W block (fragment pairs are adjacent there)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+                    *reinterpret_cast<double2*>(Wg + wg_index(kk0 + 8 * a, q0 + 8 * b)) = make_double2(acc.c[a][b][0], acc.c[a][b][1]);
+        }
+        __syncthreads();
+        DIAG_STAMP(50 + hh);
+    }
+
+    DIAG_STAMP(55);
+}
+#ifdef LSK_TRACE
+}  // namespace chol
+}  // namespace lsk
+extern "C" int lsk_debug_diag_trace(void* host) { return (int)cudaMemcpyFromSymbol(host, lsk::chol::g_diag_trace, sizeof(lsk::chol::g_diag_trace)); }
+namespace lsk {
+namespace chol {
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // row panel:  U[k0 + kk, j] = sum_q B[kk][q] A[k0 + q, j]   for the 64 columns j0 .. j0 + 63 of this CTA
@@ -430,6 +728,15 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(diag_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAGT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(W, 0, (size_t)n_blocks(n) * WBLK * sizeof(double), st);      // diag_tile_kernel writes the non-zero half of each block only
+    if (e != cudaSuccess) return (int)e;
+    static const bool sweep = [] { const char* v = getenv("LSK_DIAG_SWEEP"); return v && v[0] == '1'; }();   // development: the rank-1 sweep
+    auto diag = [&](int at, int nb, double* w) {
+        if (sweep) diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, lda, at, nb, w, info);
+        else diag_tile_kernel<<<1, DIAG_THREADS, DIAGT_SMEM, st>>>(A, lda, at, nb, w, info);
+    };
 
     constexpr int KG2 = 2 * NB / 4;                      // k-groups per row of the two-panel operand
     LskEpilogue ep = {};
@@ -441,7 +748,7 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
     for (long long k0 = 0, blk = 0; k0 < n; k0 += 2 * NB, blk += 2) {
         // ---- first panel
         const int nb1 = (int)((n - k0) < NB ? (n - k0) : NB);
-        diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, lda, (int)k0, nb1, W + blk * WBLK, info);
+        diag((int)k0, nb1, W + blk * WBLK);
         const long long s1 = k0 + NB, m1 = n - s1;
         if (m1 <= 0) break;
         trsm_kernel<<<(unsigned)(((m1 + 127) / 128) * 2), TRSM_THREADS, TRSM_SMEM, st>>>(A, lda, n, s1, n, (int)k0, W + blk * WBLK, P, KG2, 0);
@@ -452,7 +759,7 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
         int rc = lsk_pairwise_poly(P, P, strip, m1, KG2, &ep, A + s1 * lda + s1, lda, stream);
         if (rc != 0) return rc;
         // ---- second panel
-        diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, lda, (int)s1, (int)strip, W + (blk + 1) * WBLK, info);
+        diag((int)s1, (int)strip, W + (blk + 1) * WBLK);
         const long long s2 = s1 + NB, m2 = n - s2;
         if (m2 <= 0) break;
         double* P2 = P + 2ll * KG2 * 256;                // operand rows are relative to s2: two 64-row panels further
