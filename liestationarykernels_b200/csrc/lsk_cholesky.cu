@@ -290,21 +290,53 @@ diag_tile_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* 
     {
         const int r = t >> 4, c = t & 15;
         double tmp[TRI];                                      // all 36 loads in flight before the first store
+        if (nb == NB) {                                       // full block: one multiply-add of address arithmetic per load
+            const size_t row16 = 16 * (size_t)lda;
+            const double* p = A + (size_t)(k0 + r) * lda + k0 + c;
+            const double* pm = (c < r) ? A + (size_t)(k0 + c) * lda + k0 + r : p;      // mirrored position inside a diagonal tile
 #pragma unroll
-        for (int bj = 0; bj < NTL; ++bj)
+            for (int bj = 0; bj < NTL; ++bj)
 #pragma unroll
-            for (int bi = 0; bi <= bj; ++bi) {
-                int R = 16 * bi + r, C = 16 * bj + c;
-                if (bi == bj && c < r) { const int x = R; R = C; C = x; }
-                const bool in = R < nb && C < nb;                 // ragged block: read a valid entry, then select
-                const double x = A[(size_t)(k0 + (in ? R : 0)) * lda + k0 + (in ? C : 0)];
-                tmp[bj * (bj + 1) / 2 + bi] = in ? x : ((R == C) ? 1.0 : 0.0);
-            }
+                for (int bi = 0; bi <= bj; ++bi) tmp[bj * (bj + 1) / 2 + bi] = ((bi == bj) ? pm : p)[bi * row16 + 16 * bj];
+        } else {
+#pragma unroll
+            for (int bj = 0; bj < NTL; ++bj)
+#pragma unroll
+                for (int bi = 0; bi <= bj; ++bi) {
+                    int R = 16 * bi + r, C = 16 * bj + c;
+                    if (bi == bj && c < r) { const int x = R; R = C; C = x; }
+                    const bool in = R < nb && C < nb;             // ragged block: read a valid entry, then select
+                    const double x = A[(size_t)(k0 + (in ? R : 0)) * lda + k0 + (in ? C : 0)];
+                    tmp[bj * (bj + 1) / 2 + bi] = in ? x : ((R == C) ? 1.0 : 0.0);
+                }
+        }
 #pragma unroll
         for (int i = 0; i < TRI; ++i) Up[i * TILE + r * TS + c] = tmp[i];
     }
     __syncthreads();
     DIAG_STAMP(1);
+
+    auto inverse_row = [&](int bi, int first, int step) {
+        double* scratch = Tt + warp * TILE;
+        for (int bj = first; bj < bi; bj += step) {
+            TileAcc acc;
+            acc.zero();
+            for (int k = bj; k < bi; ++k) acc.mma_tn<false>(Up + ut(k, bi) * TILE, Bp + lt(k, bj) * TILE, g, tig);
+            acc.store(scratch, g, tig);
+            __syncwarp();
+            TileAcc x;
+            x.zero();
+            x.mma_nn<true>(Bp + lt(bi, bi) * TILE, scratch, g, tig);
+            __syncwarp();
+            x.store(Bp + lt(bi, bj) * TILE, g, tig);
+            const int kk0 = 16 * bi + g, q0 = 16 * bj + 2 * tig;                 // and into the W block (fragment pairs are adjacent there)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+                    *reinterpret_cast<double2*>(Wg + wg_index(kk0 + 8 * a, q0 + 8 * b)) = make_double2(x.c[a][b][0], x.c[a][b][1]);
+        }
+    };
 
 #pragma unroll 1
     for (int jb = 0; jb < NTL; ++jb) {
@@ -354,15 +386,21 @@ diag_tile_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* 
             const long long gstep = iside ? 4 : lda;
             const bool col_ok = iside || o + c < nb;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const double u = v[r] * rsv[o + r];
-                dst[r * TS] = (iside || r <= c) ? u : 0.0;
-                st_global_if(gdst + r * gstep, u, col_ok && (iside ? (r >= c) : (r <= c)));
+            for (int r = 0; r < 16; r += 2) {                    // all loads before the first store (the stores are ordered asm)
+                const double2 x = *reinterpret_cast<const double2*>(rsv + o + r);
+                v[r] *= x.x; v[r + 1] *= x.y;
             }
-        } else if (jb > 0) {
-            // ---- S3b of the previous tile row: trailing tiles below the row that S3a already served
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                dst[r * TS] = (iside || r <= c) ? v[r] : 0.0;
+                st_global_if(gdst + r * gstep, v[r], col_ok && (iside ? (r >= c) : (r <= c)));
+            }
+        } else if (jb > 0 && warp != 4) {
+            // ---- S3b of the previous tile row: trailing tiles below the row that S3a already served.  Six helpers: warp 4 sits
+            // on the sub-partition of warp 0 and its DMMAs would delay every fp64 instruction of the dependent chain of S1.
+            const int hw = warp - (warp > 4 ? 2 : 1);             // 0 .. 5
             const int rows = NTL - 1 - jb, tiles = rows * (rows + 1) / 2;
-            for (int idx = warp - 1; idx < tiles; idx += 7) {
+            for (int idx = hw; idx < tiles; idx += 6) {
                 int rem = idx, bi = jb + 1, len = rows;
                 while (rem >= len) { rem -= len; ++bi; --len; }
                 const int bj = bi + rem;
@@ -372,6 +410,9 @@ diag_tile_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* 
                 acc.mma_tn<true>(Up + ut(jb - 1, bi) * TILE, Up + ut(jb - 1, bj) * TILE, g, tig);
                 acc.store(Ct, g, tig);
             }
+            // ---- and tile row jb - 1 of B = U^{-T} (block forward substitution; everything it needs exists since S1 of that row):
+            //      B(bi, bj) = -B(bi, bi) sum_{k = bj}^{bi - 1} L(bi, k) B(k, bj),   L(bi, k) = U(k, bi)^T.   One warp per tile.
+            inverse_row(jb - 1, 5 - hw, 6);
         }
         DIAG_STAMP(2 + 6 * jb);
         __syncthreads();
@@ -413,47 +454,8 @@ diag_tile_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* 
 
     DIAG_STAMP(50);
 
-    // ---- B = U^{-T} by recursive doubling:  [B11 0; B21 B22],  B21 = -B22 L21 B11,  L21 = (U12)^T
-#pragma unroll 1
-    for (int hh = 1; hh <= 4; hh *= 2) {
-        const int per_merge = hh * hh;
-        // T[k1][bj] = sum_{k2 >= bj} L(p + h + k1, p + k2) B(p + k2, p + bj)
-        for (int slot = 0; slot < (hh == 4 ? 2 : 1); ++slot) {
-            int q, k1, bj;
-            if (hh == 1) { q = warp; k1 = 0; bj = 0; if (warp >= 4) continue; }
-            else if (hh == 2) { q = warp >> 2; k1 = (warp >> 1) & 1; bj = warp & 1; }
-            else { q = 0; k1 = slot ? 2 + (warp >> 2) : (warp >> 2); bj = slot ? 3 - (warp & 3) : (warp & 3); }
-            const int p = 2 * hh * q;
-            TileAcc acc;
-            acc.zero();
-            for (int k2 = bj; k2 < hh; ++k2)
-                acc.mma_tn<false>(Up + ut(p + k2, p + hh + k1) * TILE, Bp + lt(p + k2, p + bj) * TILE, g, tig);
-            acc.store(Tt + (q * per_merge + k1 * hh + bj) * TILE, g, tig);
-        }
-        __syncthreads();
-        // B(p + h + bi, p + bj) = - sum_{k1 <= bi} B(p + h + bi, p + h + k1) T[k1][bj]
-        for (int slot = 0; slot < (hh == 4 ? 2 : 1); ++slot) {
-            int q, bi, bj;
-            if (hh == 1) { q = warp; bi = 0; bj = 0; if (warp >= 4) continue; }
-            else if (hh == 2) { q = warp >> 2; bi = (warp >> 1) & 1; bj = warp & 1; }
-            else { q = 0; bi = slot ? 3 - (warp & 3) : (warp & 3); bj = slot ? 2 + (warp >> 2) : (warp >> 2); }
-            const int p = 2 * hh * q;
-            TileAcc acc;
-            acc.zero();
-            for (int k1 = 0; k1 <= bi; ++k1)
-                acc.mma_nn<true>(Bp + lt(p + hh + bi, p + hh + k1) * TILE, Tt + (q * per_merge + k1 * hh + bj) * TILE, g, tig);
-            acc.store(Bp + lt(p + hh + bi, p + bj) * TILE, g, tig);
-            const int kk0 = 16 * (p + hh + bi) + g, q0 = 16 * (p + bj) + 2 * tig;      // and into the W block (fragment pairs are adjacent there)
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b)
-                    *reinterpret_cast<double2*>(Wg + wg_index(kk0 + 8 * a, q0 + 8 * b)) = make_double2(acc.c[a][b][0], acc.c[a][b][1]);
-        }
-        __syncthreads();
-        DIAG_STAMP(50 + hh);
-    }
-
+    // ---- last tile row of B (rows 0 .. 6 were produced beside S1 of the following rows)
+    inverse_row(NTL - 1, warp, 8);
     DIAG_STAMP(55);
 }
 #ifdef LSK_TRACE

@@ -32,5 +32,4 @@ for jb in range(8):
     print("jb %d: S1 | S3b region %5d (warp 0 S1 alone: %5d; S3b warps max %5d)   S2 region %5d   S3a region %5d" % (
         jb, a - prev, b[0, e] - prev, (b[1:, e] - prev).max(), s2 - a, s3 - s2))
     prev = s3
-print("factor loop:", prev - rel(1), " store U:", rel(50) - prev, " levels 1/2/4:", rel(51) - rel(50), rel(52) - rel(51), rel(54) - rel(52),
-      " W store:", rel(55) - rel(54), " total:", rel(55))
+print("factor loop:", prev - rel(1), " last row of the inverse:", rel(55) - rel(50), " total:", rel(55))
