@@ -5,8 +5,8 @@
 //   A = U^T U,  U upper triangular, factorised IN PLACE in the upper triangle of a row-major matrix (equivalently: the
 //   lower factor L = U^T of the same matrix read column-major).  Right-looking, 128-column panels, two panels per
 //   trailing update (lsk_potrf_upper):
-//     diag_kernel   one CTA: U_kk = chol(A_kk) and W_kk = U_kk^{-1}, both register-resident rank-1 sweeps (each thread owns
-//                   a cyclic 4 x 8 sub-block; one row broadcast through shared memory and ONE barrier per step)
+//     diag_tile_kernel   one CTA: U_kk = chol(A_kk) and W_kk = U_kk^{-T} on 16 x 16 tiles (register-resident elimination of the
+//                   diagonal tile by one warp, DMMA tile products by the others, look-ahead; see the kernel)
 //     trsm_kernel   row panel U_k,: = W_kk^T A_k,: on the fp64 tensor-core path (DMMA), written twice: row-major into A
 //                   (the factor) and panel-major into the workspace (the operand layout of the pairwise kernel)
 //     pairwise_kernel<SYRK>  strip / trailing update A_ij -= U_ki^T U_kj (K = 128 / 256) on the tiles that reach the
@@ -17,8 +17,6 @@
 //     lsk_trsm_lower   the forward solve for a block of right-hand sides (trsm_kernel + repack_kernel + tile kernel)
 //     lsk_potri_upper  Y = U^{-T} by the same sweep on the identity and A^{-1} = sum_k Y_k^T Y_k on the triangular tile
 //                      schedule: 2 n^3 / 3 flop, the zero structure of U^{-T} used exactly at block level
-#include <cstdlib>
-
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
 
@@ -30,8 +28,6 @@ namespace chol {
 
 constexpr int NB = 128;                 // block size = K of the trailing update (32 k-groups)
 constexpr int WBLK = NB * NB;           // doubles per stored inverse block
-constexpr int SLD = NB + 1;             // padded row length of the shared-memory copy of U_kk
-constexpr int DIAG_SMEM = (NB * SLD + 2 * NB + 3 * NB) * 8;
 
 // W block layout ("k-group major", the A-operand layout of trsm_kernel):  B[kk][q] = (U^{-T})[kk][q] = W[q][kk]
 // sits at  (q / 4) * 512 + kk * 4 + q % 4.
@@ -53,126 +49,11 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // ------------------------------------------------------------------------------------------------------------
 constexpr int DIAG_THREADS = 256;
 
-__global__ void __launch_bounds__(DIAG_THREADS, 1)
-diag_kernel(double* __restrict__ A, long long lda, int k0, int nb, double* __restrict__ Wg, int* __restrict__ info)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* S = reinterpret_cast<double*>(smem_raw);          // U_kk (upper, diagonal included), row length SLD
-    double* rowbuf = S + NB * SLD;                            // 2 x NB: the broadcast pivot row, double-buffered
-    double* dpiv = rowbuf + 2 * NB;                           // pivots d_j (= U_jj^2)
-    double* udiag = dpiv + NB;                                // U_jj
-    double* uinv = udiag + NB;                                // 1 / U_jj
-    // 256 threads, each owns an 8 x 8 cyclic sub-block: rows tr + 16 i, columns tc + 16 k.  (A 4 x 8 block on 512 threads
-    // needs 12 shared-memory reads per 32 multiply-adds and twice the warps at every barrier: 66 us per block against 40.)
-    const int t = threadIdx.x, tr = t >> 4, tc = t & 15;
-
-    double a[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int r = tr + 16 * i, c = tc + 16 * k;
-            double v = (r == c) ? 1.0 : 0.0;                  // identity padding of a ragged last block
-            if (r < nb && c < nb) v = (c >= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0;
-            a[i][k] = v;
-        }
-
-    // ---- phase 1: right-looking elimination.  After step j, row j holds the unscaled U: U[j][c] = a[j][c] / sqrt(d_j).
-    // Only entries that can lie on or above the diagonal are kept up to date: column group k reaches row group i iff
-    // k >= i; rows <= j are final (i < jb).
-#pragma unroll
-    for (int jb = 0; jb < 8; ++jb) {
-#pragma unroll 1
-        for (int jj = 0; jj < 16; ++jj) {
-            const int j = 16 * jb + jj;
-            double* buf = rowbuf + (j & 1) * NB;
-            if (tr == jj) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (k >= jb) buf[tc + 16 * k] = a[jb][k];
-            }
-            __syncthreads();
-            const double d = buf[j];
-            if (t == 0) {
-                dpiv[j] = d;
-                if (!(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);   // not positive definite (LAPACK info convention)
-            }
-            const double id = fast_rcp(d);
-            double vc[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) if (k >= jb) vc[k] = buf[tc + 16 * k];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < jb) continue;
-                const int r = tr + 16 * i;
-                const double vr = (r > j) ? buf[r] * id : 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (k >= i) a[i][k] = fma(-vr, vc[k], a[i][k]);
-            }
-        }
-    }
-    __syncthreads();
-    if (t < NB) {
-        const double d = dpiv[t];
-        const double u = sqrt(d);
-        udiag[t] = u;
-        uinv[t] = 1.0 / u;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int r = tr + 16 * i, c = tc + 16 * k;
-            if (c >= r) {
-                const double u = (c == r) ? udiag[r] : a[i][k] * uinv[r];
-                S[r * SLD + c] = u;
-                if (c < nb) A[(size_t)(k0 + r) * lda + k0 + c] = u;       // c >= r, so r < nb as well
-            }
-        }
-    __syncthreads();
-
-    // ---- phase 2: B = U^{-T} by the same sweep applied to the identity:  B[j][:] /= U_jj;  B[r][:] -= U[j][r] B[j][:], r > j.
-    // Row j of B vanishes right of column j: only column groups k <= jb carry anything.  `a` is dead: its registers are reused.
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a[i][k] = (tr + 16 * i == tc + 16 * k) ? 1.0 : 0.0;
-#pragma unroll
-    for (int jb = 0; jb < 8; ++jb) {
-#pragma unroll 1
-        for (int jj = 0; jj < 16; ++jj) {
-            const int j = 16 * jb + jj;
-            double* buf = rowbuf + (j & 1) * NB;
-            if (tr == jj) {
-                const double s = uinv[j];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (k <= jb) { a[jb][k] *= s; buf[tc + 16 * k] = a[jb][k]; }
-            }
-            __syncthreads();
-            double vc[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) if (k <= jb) vc[k] = buf[tc + 16 * k];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < jb) continue;
-                const int r = tr + 16 * i;
-                const double ur = (r > j) ? S[j * SLD + r] : 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (k <= jb) a[i][k] = fma(-ur, vc[k], a[i][k]);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) Wg[wg_index(tr + 16 * i, tc + 16 * k)] = a[i][k];
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// diagonal block, tiled: the same results (U_kk and B = U_kk^{-T}) with the dependent chain cut to what it has to be.
+// U_kk = chol(A_kk) and B = U_kk^{-T} of one 128 x 128 diagonal block, one CTA, with the dependent chain cut to what it has to be.
 //
-// The sweep above pays a CTA-wide barrier, a shared-memory round trip and a reciprocal on the dependent path of each of
-// its 2 x 128 steps (~190 ns per step).  Here the block is cut into 16 x 16 tiles (only the 36 on or above the diagonal are
+// (Round 1 swept the block with 2 x 128 rank-1 steps, each paying a CTA-wide barrier, a shared-memory round trip and a
+// reciprocal on its dependent path: ~190 ns per step, 52 us per block.)  The block is cut into 16 x 16 tiles (only the 36 on or above the diagonal are
 // kept, each in shared memory with row stride 18), and per tile row jb:
 //   S1  one warp eliminates the 16 x 16 diagonal tile in registers: lane c < 16 owns column c of the (symmetric) tile, lane
 //       16 + c owns column c of an identity that receives the same row operations.  The pivot row reaches the lanes by warp
@@ -726,19 +607,13 @@ extern "C" int lsk_potrf_upper(void* A_, long long n, long long lda, void* work_
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     if (n == 0) return 0;
-    e = cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
-    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(diag_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAGT_SMEM);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(W, 0, (size_t)n_blocks(n) * WBLK * sizeof(double), st);      // diag_tile_kernel writes the non-zero half of each block only
     if (e != cudaSuccess) return (int)e;
-    static const bool sweep = [] { const char* v = getenv("LSK_DIAG_SWEEP"); return v && v[0] == '1'; }();   // development: the rank-1 sweep
-    auto diag = [&](int at, int nb, double* w) {
-        if (sweep) diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, lda, at, nb, w, info);
-        else diag_tile_kernel<<<1, DIAG_THREADS, DIAGT_SMEM, st>>>(A, lda, at, nb, w, info);
-    };
+    auto diag = [&](int at, int nb, double* w) { diag_tile_kernel<<<1, DIAG_THREADS, DIAGT_SMEM, st>>>(A, lda, at, nb, w, info); };
 
     constexpr int KG2 = 2 * NB / 4;                      // k-groups per row of the two-panel operand
     LskEpilogue ep = {};
