@@ -45,31 +45,29 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// diagonal block
-// ------------------------------------------------------------------------------------------------------------
-constexpr int DIAG_THREADS = 256;
-
-// ------------------------------------------------------------------------------------------------------------
-// U_kk = chol(A_kk) and B = U_kk^{-T} of one 128 x 128 diagonal block, one CTA, with the dependent chain cut to what it has to be.
+// diagonal block:  U_kk = chol(A_kk) and B = U_kk^{-T} of one 128 x 128 block, one CTA, the dependent chain cut to what it has to be
 //
 // (Round 1 swept the block with 2 x 128 rank-1 steps, each paying a CTA-wide barrier, a shared-memory round trip and a
-// reciprocal on its dependent path: ~190 ns per step, 52 us per block.)  The block is cut into 16 x 16 tiles (only the 36 on or above the diagonal are
-// kept, each in shared memory with row stride 18), and per tile row jb:
+// reciprocal on its dependent path: ~190 ns per step, 52 us per block; this kernel: 23.7 us, profiles/diag_trace_r02.txt.)
+// The block is cut into 16 x 16 tiles (the 36 on or above the diagonal, row stride 18 in shared memory), and per tile row jb:
 //   S1  one warp eliminates the 16 x 16 diagonal tile in registers: lane c < 16 owns column c of the (symmetric) tile, lane
-//       16 + c owns column c of an identity that receives the same row operations.  The pivot row reaches the lanes by warp
-//       shuffles from lane j (its column IS the pivot row); the update is  v_r -= (D_rj D_jc) / d_j  with the product formed
-//       before 1 / d_j is known, so a step's dependent path is shuffle -> reciprocal -> one fused multiply-add and there is
-//       no barrier inside the 16 steps.  Out come U_jj = diag(d^-1/2) R and, from the identity side, its inverse transpose
+//       16 + c owns column c of an identity that receives the same row operations.  The pivot row is spread over the lanes and
+//       all-gathered through shared memory; the update is  v_r -= (D_jr D_jc) / d_j  with the product formed before 1 / d_j is
+//       known, so a step's dependent path is store -> load -> reciprocal -> one fused multiply-add, and there is no barrier inside
+//       the 16 steps.  Out come U_jj = diag(d^-1/2) R and, from the identity side, its inverse transpose
 //       B_jj = diag(d^-1/2) L_unit^{-1} - no separate inversion of the diagonal tiles.
 //   S2  the tile row right of it, U_j,: = B_jj A_j,: - one 16 x 16 x 16 product per warp on the fp64 tensor-core path,
 //   S3a the next tile row receives its rank-16 update (so that S1 of the next tile can start),
-//   S3b the rest of the trailing tiles are updated by warps 1-7 WHILE warp 0 runs S1 of the next tile (look-ahead).
-//   The off-diagonal tiles of B follow by recursive doubling, B_21 = -B_22 L_21 B_11 at tile sizes 16, 32, 64: products of
-//   16 x 16 tiles spread over the eight warps, six barriers in all.
+//   S3b WHILE warp 0 runs S1 of the next tile, six helper warps update the rest of the trailing tiles and compute tile row
+//       jb of B by block forward substitution, B(i, j) = -B(i, i) sum_k U(k, i)^T B(k, j) (one warp per tile).  The seventh warp
+//       shares warp 0's sub-partition and idles: its DMMAs would delay every fp64 instruction of the dependent chain.
+//   The factor and the non-zero half of B go to global memory tile by tile as they are finished (the zeros of the W block come
+//   from a memset of the workspace): a lone SM drains 17-24 bytes per clock, 205 KB at the end of the kernel cost 12 000 cycles.
 // Every tile product is DMMA.8x8x4: with plain DFMA a 2 x 4 register block per lane needs three 16-byte shared-memory loads
 // per eight multiply-adds and the ONE shared-memory pipe of the SM (not the fp64 pipe) sets the pace - measured 1 480 cycles
 // per tile product; the DMMA fragments need four 8-byte loads per 1 024 multiply-adds.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int DIAG_THREADS = 256;
 constexpr int TS = 18;                           // row stride of a 16 x 16 tile in shared memory (doubles)
 constexpr int TILE = 16 * TS;
 constexpr int NTL = NB / 16;                     // tiles per side
