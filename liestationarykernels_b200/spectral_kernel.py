@@ -305,12 +305,12 @@ class EigenbasisSumKernel(AbstractSpectralKernel):
         if rb <= 0 or rb % 128:
             raise ValueError("row_block must be a positive multiple of 128")
         with torch.no_grad():
-            if self.training and normalize:
-                self.compute_normalizer()
             if not isinstance(manifold, CompactLieGroup) or N <= rb or M == 0:
                 if N and M:
                     out.copy_(self.forward(xd, yd, normalize=normalize))
                 return out
+            if self.training and normalize:
+                self.compute_normalizer()                 # as `forward` does (one draw from the generator per call)
             plan = manifold.plan
             ep = self._epilogue(normalize)
             ea, eb = ops.embed_pair(plan, xd, yd)
