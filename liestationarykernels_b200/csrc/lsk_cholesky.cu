@@ -12,8 +12,8 @@
 //     pairwise_kernel<SYRK>  strip / trailing update A_ij -= U_ki^T U_kj (K = 128 / 256) on the tiles that reach the
 //                   diagonal or lie above it (lsk_pairwise.cu: TMA ring + DMMA, read-modify-write epilogue)
 //   The inverses W_kk stay in the workspace:
-//     lsk_potrs_upper  U^T y = b, U x = y: one 128 x 128 matrix-vector product per block plus a panel update
-//                      (block_matvec_kernel + fwd/bwd_update_kernel), no divisions, no dependent chains
+//     lsk_potrs_upper  U^T y = b, U x = y: one launch per sweep (sweep_kernel): every block owned by one CTA, solved with its
+//                      inverse block, the blocks pipelined across the SMs through flags - no divisions, no grid-wide barriers
 //     lsk_trsm_lower   the forward solve for a block of right-hand sides (trsm_kernel + repack_kernel + tile kernel)
 //     lsk_potri_upper  Y = U^{-T} by the same sweep on the identity and A^{-1} = sum_k Y_k^T Y_k on the triangular tile
 //                      schedule: 2 n^3 / 3 flop, the zero structure of U^{-T} used exactly at block level
@@ -434,99 +434,111 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n_rows, long long c
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// triangular solves with one right-hand side, one launch per block
+// triangular solves with one right-hand side: one launch per sweep, the blocks pipelined across the SMs
 // ------------------------------------------------------------------------------------------------------------
-// Block step of the triangular solves, two launches:
-//   block_matvec_kernel (one CTA)   z = B r_k (forward, B = U_kk^{-T}) or z = B^T r_k (backward); z is the solution block
-//   fwd_update_kernel               r_j -= U[k-rows, j]^T z   for the columns j behind the block
-//   bwd_update_kernel               r_i -= U[i, k-cols] z     for the rows i above the block
-// (One fused launch per block made every CTA repeat the 128 x 128 matrix-vector product: 256 CTAs x 128 KB through L2 per
-// step, 26 us per block; split: 20 us.  Plain stream-ordered launches: programmatic dependent launches gained 1 % here.)
-__global__ void __launch_bounds__(512)
-block_matvec_kernel(const double* __restrict__ Wg, const double* __restrict__ r, int k0, int nb, int transpose,
-                    double* __restrict__ z_out /* [128] scratch */, double* __restrict__ sol /* solution vector */)
-{
-    __shared__ double rk[NB];
-    const int t = threadIdx.x;
-    if (t < NB) rk[t] = t < nb ? r[k0 + t] : 0.0;
-    __syncthreads();
-    const int row = t >> 2, sub = t & 3;             // four threads per output entry
-    double acc = 0.0;
-    if (!transpose) {                                // z[kk] = sum_{q <= kk} B[kk][q] r[q]; k-groups g = sub, sub + 4, ...
-        for (int g = sub; g <= (row >> 2); g += 4) {
-            const double2* w = reinterpret_cast<const double2*>(Wg + g * (NB * 4) + row * 4);
-            const double2 w0 = w[0], w1 = w[1];
-            acc = fma(w0.x, rk[4 * g], acc); acc = fma(w0.y, rk[4 * g + 1], acc);
-            acc = fma(w1.x, rk[4 * g + 2], acc); acc = fma(w1.y, rk[4 * g + 3], acc);
-        }
-    } else {                                         // z[q] = sum_{kk >= q} B[kk][q] r[kk]
-        const double* w = Wg + (row >> 2) * (NB * 4) + (row & 3);
-        for (int kk = row + sub; kk < NB; kk += 4) acc = fma(w[kk * 4], rk[kk], acc);
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (sub == 0) {
-        z_out[row] = acc;
-        if (row < nb) sol[k0 + row] = acc;
-    }
-}
+// U^T y = b (forward) or U x = y (backward) over the 128-row blocks.  Round 1 ran a block step as two stream-ordered launches
+// (the 128 x 128 product with the stored inverse block, then the update of the rest of the vector): 4 n / 128 dependent launches,
+// 5.2 ms at n = 16384 for 2 GB of reads.  Here block j belongs to ONE CTA, which keeps the running right-hand side of its block
+// in shared memory, applies the contributions of the earlier blocks in the order they are finished (the 128 x 128 tile of U is
+// requested BEFORE the CTA waits for that block's solution, so on the dependent path the tile is already in registers), solves
+// with the inverse block (staged in shared memory at the start), writes its 128 entries of the solution in place and raises a
+// flag.  No grid-wide barrier: a step of the dependent chain is flag -> 128 values from L2 -> two 128 x 128 products.
+// CTAs take their position in the sweep from a ticket, so a CTA only ever waits for CTAs that started before it.
+constexpr int SWEEP_THREADS = 512;
+constexpr int SWEEP_SMEM = (WBLK + 2 * NB + 4 * NB) * 8 + 16;
 
-// CTA = 64 columns x 4 slices of the block's rows (32 each), reduced through shared memory.
-__global__ void __launch_bounds__(256)
-fwd_update_kernel(const double* __restrict__ U, long long lda, long long n, int k0, int nb, const double* __restrict__ zg,
-                  double* __restrict__ r)
+template <bool BACKWARD>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+sweep_kernel(const double* __restrict__ U, long long lda, long long n, const double* __restrict__ Wall, double* b,
+             int* flags, int* ticket, int nblk)
 {
-    __shared__ double z[NB], part[4][64];
-    const int t = threadIdx.x;
-    if (t < NB) z[t] = zg[t];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Ws = reinterpret_cast<double*>(smem_raw);         // inverse block of the block being solved, global layout (wg_index)
+    double* zs = Ws + WBLK;                                   // solution of the source block
+    double* bj = zs + NB;                                     // running right-hand side of this CTA's block
+    double* part = bj + NB;                                   // 4 x NB partial sums
+    int* vid_s = reinterpret_cast<int*>(part + 4 * NB);
+    const int t = threadIdx.x, lo = t & (NB - 1), q4 = t >> 7;
+    if (t == 0) *vid_s = atomicAdd(ticket, 1);
     __syncthreads();
-    const int tx = t & 63, ty = t >> 6;
-    const long long j = (long long)k0 + nb + 64ll * blockIdx.x + tx;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (j < n) {
-        const double* col = U + (size_t)(k0 + 32 * ty) * lda + j;
-        const double* zz = z + 32 * ty;
-        const int lim = min(32, nb - 32 * ty);
-        int kk = 0;
-#pragma unroll 2
-        for (; kk + 3 < lim; kk += 4) {
-            a0 = fma(col[(size_t)kk * lda], zz[kk], a0);
-            a1 = fma(col[(size_t)(kk + 1) * lda], zz[kk + 1], a1);
-            a2 = fma(col[(size_t)(kk + 2) * lda], zz[kk + 2], a2);
-            a3 = fma(col[(size_t)(kk + 3) * lda], zz[kk + 3], a3);
-        }
-        for (; kk < lim; ++kk) a0 = fma(col[(size_t)kk * lda], zz[kk], a0);
-    }
-    part[ty][tx] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (ty == 0 && j < n) r[j] -= (part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx]);
-}
+    const int vid = *vid_s, G = gridDim.x;
 
-// CTA = 64 rows, 4 threads per row (32 contiguous doubles each), reduced by shuffles.
-__global__ void __launch_bounds__(256)
-bwd_update_kernel(const double* __restrict__ U, long long lda, int k0, int nb, const double* __restrict__ zg, double* __restrict__ r)
-{
-    __shared__ double z[NB];
-    const int t = threadIdx.x;
-    if (t < NB) z[t] = zg[t];
-    __syncthreads();
-    const int sub = t & 3;
-    const long long i = 64ll * blockIdx.x + (t >> 2);
-    double acc0 = 0.0, acc1 = 0.0;
-    if (i < k0) {
-        const double* row = U + (size_t)i * lda + k0 + 32 * sub;
-        const int lim = min(32, nb - 32 * sub);
-#pragma unroll 8
-        for (int q = 0; q + 1 < lim; q += 2) {
-            acc0 = fma(row[q], z[32 * sub + q], acc0);
-            acc1 = fma(row[q + 1], z[32 * sub + q + 1], acc1);
+    for (int s = vid; s < nblk; s += G) {
+        const int j = BACKWARD ? nblk - 1 - s : s;
+        const long long j0 = (long long)j * NB;
+        const int nbj = (int)((n - j0) < NB ? (n - j0) : NB);
+        __syncthreads();                                      // previous round: Ws / bj no longer read
+        {
+            const double2* src = reinterpret_cast<const double2*>(Wall + (size_t)j * WBLK);
+            double2* dst = reinterpret_cast<double2*>(Ws);
+#pragma unroll 4
+            for (int i = t; i < WBLK / 2; i += SWEEP_THREADS) dst[i] = src[i];
         }
-        if (lim > 0 && (lim & 1)) acc0 = fma(row[lim - 1], z[32 * sub + lim - 1], acc0);
+        if (t < NB) bj[t] = (t < nbj) ? __ldcg(b + j0 + t) : 0.0;
+
+        for (int i = 0; i < s; ++i) {
+            const int k = BACKWARD ? nblk - 1 - i : i;        // source block, finished (or being finished) by an earlier CTA
+            const long long k0 = (long long)k * NB;
+            const int nbk = (int)((n - k0) < NB ? (n - k0) : NB);
+            // the tile of U that couples block k to block j, requested before the wait
+            double u[32];
+            if (!BACKWARD) {                                  // rows k0 + 32 q4 + r (a full block: k < j), column j0 + lo
+                const double* src = U + (size_t)(k0 + 32 * q4) * lda + j0 + lo;
+                const bool ok = lo < nbj;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) u[r] = ok ? src[(size_t)r * lda] : 0.0;
+            } else {                                          // row j0 + lo (a full block: j < k), columns k0 + 32 q4 + c
+                const double* src = U + (size_t)(j0 + lo) * lda + k0 + 32 * q4;
+                const int lim = nbk - 32 * q4;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) u[c] = (c < lim) ? src[c] : 0.0;
+            }
+            if (t == 0) {
+                int v = 0;
+                long long spins = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + k) : "memory");
+                } while (v == 0 && ++spins < (1ll << 30));    // bounded: a lost flag must not hang the device
+            }
+            __syncthreads();                                  // also: zs / part of the previous step are no longer read
+            if (t < NB) zs[t] = (t < nbk) ? __ldcg(b + k0 + t) : 0.0;
+            __syncthreads();
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 32; r += 2) {
+                acc0 = fma(u[r], zs[32 * q4 + r], acc0);
+                acc1 = fma(u[r + 1], zs[32 * q4 + r + 1], acc1);
+            }
+            part[q4 * NB + lo] = acc0 + acc1;
+            __syncthreads();
+            if (t < NB) bj[t] -= (part[t] + part[NB + t]) + (part[2 * NB + t] + part[3 * NB + t]);
+        }
+        __syncthreads();
+        // the block itself: forward z[kk] = sum_{q <= kk} B[kk][q] r[q], backward z[q] = sum_{kk >= q} B[kk][q] r[kk]   (B = U_jj^{-T})
+        {
+            const int row = t >> 2, sub = t & 3;              // four threads per entry
+            double acc = 0.0;
+            if (!BACKWARD) {
+                for (int g = sub; g <= (row >> 2); g += 4) {
+                    const double2* w = reinterpret_cast<const double2*>(Ws + g * (NB * 4) + row * 4);
+                    const double2 w0 = w[0], w1 = w[1];
+                    acc = fma(w0.x, bj[4 * g], acc); acc = fma(w0.y, bj[4 * g + 1], acc);
+                    acc = fma(w1.x, bj[4 * g + 2], acc); acc = fma(w1.y, bj[4 * g + 3], acc);
+                }
+            } else {
+                const double* w = Ws + (row >> 2) * (NB * 4) + (row & 3);
+                for (int kk = row + sub; kk < NB; kk += 4) acc = fma(w[kk * 4], bj[kk], acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (sub == 0 && row < nbj) b[j0 + row] = acc;
+        }
+        __syncthreads();
+        if (t == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(flags + j), "r"(1) : "memory");
+        }
     }
-    double tot = acc0 + acc1;
-    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-    if (sub == 0 && i < k0) r[i] -= tot;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -662,33 +674,24 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
     const double* U = static_cast<const double*>(U_);
     const double* W = static_cast<const double*>(work_);
     double* b = static_cast<double*>(b_);
-    double* tmp = static_cast<double*>(tmp_);
     const long long nblk = n_blocks(n);
-    double* cur = b;      // residual vector that is consumed
-    double* oth = tmp;    // solution vector that is produced
-    double* zbuf = tmp + n;                                         // the 128 doubles behind the caller's scratch vector
+    // flags (one per block and sweep) and the two tickets live in the caller's scratch vector
+    int* flags = static_cast<int*>(tmp_);
+    const size_t words = (size_t)(2 * nblk + 2);
+    if (words * sizeof(int) > (size_t)(n + 128) * sizeof(double)) return LSK_ESIZE;
+    cudaError_t e = cudaMemsetAsync(flags, 0, words * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)(nblk < sms ? nblk : sms);
     if (which & 1) {
-        for (long long blk = 0; blk < nblk; ++blk) {
-            const long long k0 = blk * NB;
-            const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
-            const long long m = n - k0 - nb;
-            block_matvec_kernel<<<1, 512, 0, st>>>(W + blk * WBLK, cur, (int)k0, nb, 0, zbuf, oth);
-            if (m > 0) fwd_update_kernel<<<(unsigned)((m + 63) / 64), 256, 0, st>>>(U, lda, n, (int)k0, nb, zbuf, cur);
-        }
-        double* sw = cur; cur = oth; oth = sw;
+        if ((e = cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM)) != cudaSuccess) return (int)e;
+        sweep_kernel<false><<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(U, lda, n, W, b, flags, flags + 2 * nblk, (int)nblk);
     }
     if (which & 2) {
-        for (long long blk = nblk - 1; blk >= 0; --blk) {
-            const long long k0 = blk * NB;
-            const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
-            block_matvec_kernel<<<1, 512, 0, st>>>(W + blk * WBLK, cur, (int)k0, nb, 1, zbuf, oth);
-            if (k0 > 0) bwd_update_kernel<<<(unsigned)((k0 + 63) / 64), 256, 0, st>>>(U, lda, (int)k0, nb, zbuf, cur);
-        }
-        double* sw = cur; cur = oth; oth = sw;
-    }
-    if (cur != b) {
-        cudaError_t e = cudaMemcpyAsync(b, cur, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM)) != cudaSuccess) return (int)e;
+        sweep_kernel<true><<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(U, lda, n, W, b, flags + nblk, flags + 2 * nblk + 1, (int)nblk);
     }
     return (int)cudaGetLastError();
 }

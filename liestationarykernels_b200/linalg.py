@@ -67,12 +67,11 @@ class CholeskyFactor:
         vec = b.dim() == 1
         cols = b.to(F64).reshape(self.n, -1).t().contiguous().clone()      # [k, n]: one contiguous vector per column
         tmp = torch.empty(self.n + 128, dtype=F64, device=self.matrix.device)
-        blocks = (self.n + 127) // 128
         for c in range(cols.shape[0] if self.n else 0):
             _lib.check(lib.lsk_potrs_upper(_lib.ptr(self.matrix), self.n, self.matrix.stride(0),
                                            _lib.ptr(self.work), _lib.ptr(cols[c]), _lib.ptr(tmp), which, _lib.stream_ptr()),
                        "lsk_potrs_upper")
-            _lib.count_launch(blocks * (2 if which == 3 else 1))
+            _lib.count_launch(2 if which == 3 else 1)
         out = cols.t().contiguous()
         return out[:, 0] if vec else out
 
