@@ -75,15 +75,20 @@ class CholeskyFactor:
         out = cols.t().contiguous()
         return out[:, 0] if vec else out
 
-    MANY_RHS = 24      # from this many right-hand sides on, `solve` goes through the dense inverse (see below)
+    def many_rhs(self) -> int:
+        """From this many right-hand sides on, `solve` goes through the dense inverse: the inverse costs 2 n^3 / 3 flop once (99 ms at
+        n = 16384, 2.9 ms at 4096) against one pipelined pair of sweeps per column (1.8 ms / 0.5 ms), so the break-even grows
+        with n; a cached inverse is always used."""
+        if getattr(self, "_inverse_panel", None) is not None:
+            return 2
+        return max(8, self.n // 256)
 
     def solve(self, b: torch.Tensor) -> torch.Tensor:
-        """A^{-1} b (LAPACK dpotrs).  A vector or a few columns: two sweeps of per-block matrix-vector steps per column
-        (`lsk_potrs_upper`, 2 x n / 128 dependent launches each).  Many columns: the backward sweep U X = Y has no blocked
-        many-right-hand-side kernel yet, so the dense inverse (`lsk_potri_upper`, 2 n^3 / 3 flop on the tensor-core tile kernel,
-        cached on the factor) is applied with one Gram launch, X = A^{-1} B: at n = 16384 that is 99 ms + 16 us per column
-        against 5.3 ms per column."""
-        if b.dim() == 2 and b.shape[1] >= self.MANY_RHS and self.n:
+        """A^{-1} b (LAPACK dpotrs).  A vector or a few columns: two pipelined sweeps per column (`lsk_potrs_upper`: one launch per
+        sweep, 1.8 ms at n = 16384).  Many columns: the backward sweep U X = Y has no blocked many-right-hand-side kernel, so the
+        dense inverse (`lsk_potri_upper`, 2 n^3 / 3 flop on the tensor-core tile kernel, cached on the factor) is applied with one
+        Gram launch, X = A^{-1} B."""
+        if b.dim() == 2 and b.shape[1] >= self.many_rhs() and self.n:
             from . import ops
             if b.shape[0] != self.n:
                 raise ValueError("right-hand side must have %d rows" % self.n)

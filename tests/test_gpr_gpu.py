@@ -318,7 +318,7 @@ def test_likelihood_and_mll_are_pure_and_idempotent():
 
 @pytest.mark.parametrize("n,k", [(300, 24), (1000, 129), (517, 64)])
 def test_solve_with_many_right_hand_sides(n, k):
-    """A^{-1} B for a block of right-hand sides (dense-inverse + Gram path from 24 columns on) against the per-column sweeps and
+    """A^{-1} B for a block of right-hand sides (dense-inverse + Gram path from max(8, n / 256) columns on) against the per-column sweeps and
     against the residual"""
     from liestationarykernels_b200.linalg import CholeskyFactor
     torch.manual_seed(n + k)
