@@ -445,7 +445,7 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n_rows, long long c
 // flag.  No grid-wide barrier: a step of the dependent chain is flag -> 128 values from L2 -> two 128 x 128 products.
 // CTAs take their position in the sweep from a ticket, so a CTA only ever waits for CTAs that started before it.
 constexpr int SWEEP_THREADS = 512;
-constexpr int SWEEP_SMEM = (WBLK + 2 * NB + 4 * NB) * 8 + 16;
+constexpr int SWEEP_SMEM = (WBLK + 2 * NB + 8 * NB) * 8 + 16;
 
 template <bool BACKWARD>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
@@ -456,12 +456,13 @@ sweep_kernel(const double* __restrict__ U, long long lda, long long n, const dou
     double* Ws = reinterpret_cast<double*>(smem_raw);         // inverse block of the block being solved, global layout (wg_index)
     double* zs = Ws + WBLK;                                   // solution of the source block
     double* bj = zs + NB;                                     // running right-hand side of this CTA's block
-    double* part = bj + NB;                                   // 4 x NB partial sums
-    int* vid_s = reinterpret_cast<int*>(part + 4 * NB);
+    double* part = bj + NB;                                   // up to 8 x NB partial sums
+    int* vid_s = reinterpret_cast<int*>(part + 8 * NB);
     const int t = threadIdx.x, lo = t & (NB - 1), q4 = t >> 7;
     if (t == 0) *vid_s = atomicAdd(ticket, 1);
     __syncthreads();
     const int vid = *vid_s, G = gridDim.x;
+    const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0);      // rows start on 16-byte boundaries
 
     for (int s = vid; s < nblk; s += G) {
         const int j = BACKWARD ? nblk - 1 - s : s;
@@ -480,18 +481,42 @@ sweep_kernel(const double* __restrict__ U, long long lda, long long n, const dou
             const int k = BACKWARD ? nblk - 1 - i : i;        // source block, finished (or being finished) by an earlier CTA
             const long long k0 = (long long)k * NB;
             const int nbk = (int)((n - k0) < NB ? (n - k0) : NB);
-            // the tile of U that couples block k to block j, requested before the wait
+            // The tile of U that couples block k to block j, requested before the wait.  16-byte loads when the matrix allows
+            // (ncu on the 8-byte version: 57 stall cycles per issue on the load-store queue, lg_throttle).
             double u[32];
-            if (!BACKWARD) {                                  // rows k0 + 32 q4 + r (a full block: k < j), column j0 + lo
-                const double* src = U + (size_t)(k0 + 32 * q4) * lda + j0 + lo;
-                const bool ok = lo < nbj;
+            if (!BACKWARD) {                                  // rows of block k (a full block: k < j), columns of block j
+                if (vec) {                                    // thread: columns 2 c2, 2 c2 + 1; rows 16 r8 .. 16 r8 + 15
+                    const int c2 = t & 63, r8 = t >> 6;
+                    const double* src = U + (size_t)(k0 + 16 * r8) * lda + j0 + 2 * c2;
+                    const bool ok0 = 2 * c2 < nbj, ok1 = 2 * c2 + 1 < nbj;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) u[r] = ok ? src[(size_t)r * lda] : 0.0;
+                    for (int r = 0; r < 16; ++r) {
+                        double2 x = make_double2(0.0, 0.0);
+                        if (ok1) x = *reinterpret_cast<const double2*>(src + (size_t)r * lda);
+                        else if (ok0) x.x = src[(size_t)r * lda];
+                        u[2 * r] = x.x; u[2 * r + 1] = x.y;
+                    }
+                } else {                                      // thread: column lo, rows 32 q4 .. 32 q4 + 31
+                    const double* src = U + (size_t)(k0 + 32 * q4) * lda + j0 + lo;
+                    const bool ok = lo < nbj;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) u[r] = ok ? src[(size_t)r * lda] : 0.0;
+                }
             } else {                                          // row j0 + lo (a full block: j < k), columns k0 + 32 q4 + c
                 const double* src = U + (size_t)(j0 + lo) * lda + k0 + 32 * q4;
                 const int lim = nbk - 32 * q4;
+                if (vec) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) u[c] = (c < lim) ? src[c] : 0.0;
+                    for (int c = 0; c < 32; c += 2) {
+                        double2 x = make_double2(0.0, 0.0);
+                        if (c + 1 < lim) x = *reinterpret_cast<const double2*>(src + c);
+                        else if (c < lim) x.x = src[c];
+                        u[c] = x.x; u[c + 1] = x.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) u[c] = (c < lim) ? src[c] : 0.0;
+                }
             }
             if (t == 0) {
                 int v = 0;
@@ -503,15 +528,35 @@ sweep_kernel(const double* __restrict__ U, long long lda, long long n, const dou
             __syncthreads();                                  // also: zs / part of the previous step are no longer read
             if (t < NB) zs[t] = (t < nbk) ? __ldcg(b + k0 + t) : 0.0;
             __syncthreads();
-            double acc0 = 0.0, acc1 = 0.0;
+            if (!BACKWARD && vec) {                           // two columns x 16 rows per thread: eight partial sums per column
+                const int c2 = t & 63, r8 = t >> 6;
+                double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-            for (int r = 0; r < 32; r += 2) {
-                acc0 = fma(u[r], zs[32 * q4 + r], acc0);
-                acc1 = fma(u[r + 1], zs[32 * q4 + r + 1], acc1);
+                for (int r = 0; r < 16; ++r) {
+                    const double z = zs[16 * r8 + r];
+                    acc0 = fma(u[2 * r], z, acc0);
+                    acc1 = fma(u[2 * r + 1], z, acc1);
+                }
+                part[r8 * NB + 2 * c2] = acc0;
+                part[r8 * NB + 2 * c2 + 1] = acc1;
+                __syncthreads();
+                if (t < NB) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) sum += part[q * NB + t];
+                    bj[t] -= sum;
+                }
+            } else {
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 32; r += 2) {
+                    acc0 = fma(u[r], zs[32 * q4 + r], acc0);
+                    acc1 = fma(u[r + 1], zs[32 * q4 + r + 1], acc1);
+                }
+                part[q4 * NB + lo] = acc0 + acc1;
+                __syncthreads();
+                if (t < NB) bj[t] -= (part[t] + part[NB + t]) + (part[2 * NB + t] + part[3 * NB + t]);
             }
-            part[q4 * NB + lo] = acc0 + acc1;
-            __syncthreads();
-            if (t < NB) bj[t] -= (part[t] + part[NB + t]) + (part[2 * NB + t] + part[3 * NB + t]);
         }
         __syncthreads();
         // the block itself: forward z[kk] = sum_{q <= kk} B[kk][q] r[q], backward z[q] = sum_{kk >= q} B[kk][q] r[kk]   (B = U_jj^{-T})

@@ -77,7 +77,7 @@ class CholeskyFactor:
 
     def many_rhs(self) -> int:
         """From this many right-hand sides on, `solve` goes through the dense inverse: the inverse costs 2 n^3 / 3 flop once (99 ms at
-        n = 16384, 2.9 ms at 4096) against one pipelined pair of sweeps per column (1.8 ms / 0.5 ms), so the break-even grows
+        n = 16384, 2.9 ms at 4096) against one pipelined pair of sweeps per column (1.25 ms / 0.42 ms), so the break-even grows
         with n; a cached inverse is always used."""
         if getattr(self, "_inverse_panel", None) is not None:
             return 2
@@ -85,7 +85,7 @@ class CholeskyFactor:
 
     def solve(self, b: torch.Tensor) -> torch.Tensor:
         """A^{-1} b (LAPACK dpotrs).  A vector or a few columns: two pipelined sweeps per column (`lsk_potrs_upper`: one launch per
-        sweep, 1.8 ms at n = 16384).  Many columns: the backward sweep U X = Y has no blocked many-right-hand-side kernel, so the
+        sweep, 1.25 ms at n = 16384).  Many columns: the backward sweep U X = Y has no blocked many-right-hand-side kernel, so the
         dense inverse (`lsk_potri_upper`, 2 n^3 / 3 flop on the tensor-core tile kernel, cached on the factor) is applied with one
         Gram launch, X = A^{-1} B."""
         if b.dim() == 2 and b.shape[1] >= self.many_rhs() and self.n:
