@@ -17,6 +17,8 @@
 //     lsk_trsm_lower   the forward solve for a block of right-hand sides (trsm_kernel + repack_kernel + tile kernel)
 //     lsk_potri_upper  Y = U^{-T} by the same sweep on the identity and A^{-1} = sum_k Y_k^T Y_k on the triangular tile
 //                      schedule: 2 n^3 / 3 flop, the zero structure of U^{-T} used exactly at block level
+#include <cstdlib>
+
 #include "lsk_common.cuh"
 #include "lsk_pairwise.cuh"
 
@@ -443,7 +445,7 @@ trsm_kernel(double* __restrict__ A, long long lda, long long n_rows, long long c
 // requested BEFORE the CTA waits for that block's solution, so on the dependent path the tile is already in registers), solves
 // with the inverse block (staged in shared memory at the start), writes its 128 entries of the solution in place and raises a
 // flag.  No grid-wide barrier: a step of the dependent chain is flag -> 128 values from L2 -> two 128 x 128 products.
-// CTAs take their position in the sweep from a ticket, so a CTA only ever waits for CTAs that started before it.
+// CTAs take their positions in the sweep from a ticket, so a CTA only ever waits for CTAs that started before it.
 constexpr int SWEEP_THREADS = 512;
 constexpr int SWEEP_SMEM = (WBLK + 2 * NB + 8 * NB) * 8 + 16;
 
@@ -459,12 +461,16 @@ sweep_kernel(const double* __restrict__ U, long long lda, long long n, const dou
     double* part = bj + NB;                                   // up to 8 x NB partial sums
     int* vid_s = reinterpret_cast<int*>(part + 8 * NB);
     const int t = threadIdx.x, lo = t & (NB - 1), q4 = t >> 7;
-    if (t == 0) *vid_s = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int vid = *vid_s, G = gridDim.x;
     const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0);      // rows start on 16-byte boundaries
 
-    for (int s = vid; s < nblk; s += G) {
+    for (;;) {
+        // Sweep positions are handed out by a ticket, one per round: whoever holds position s only waits for positions < s, and
+        // those were all taken by CTAs that are running or done - no CTA ever waits for one that has not started, whatever
+        // share of the device this launch gets.
+        if (t == 0) *vid_s = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int s = *vid_s;
+        if (s >= nblk) break;
         const int j = BACKWARD ? nblk - 1 - s : s;
         const long long j0 = (long long)j * NB;
         const int nbj = (int)((n - j0) < NB ? (n - j0) : NB);
@@ -523,7 +529,7 @@ sweep_kernel(const double* __restrict__ U, long long lda, long long n, const dou
                 long long spins = 0;
                 do {
                     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + k) : "memory");
-                } while (v == 0 && ++spins < (1ll << 30));    // bounded: a lost flag must not hang the device
+                } while (v == 0 && ++spins < (1ll << 25));    // bounded (tens of seconds): a lost flag must not hang the device
             }
             __syncthreads();                                  // also: zs / part of the previous step are no longer read
             if (t < NB) zs[t] = (t < nbk) ? __ldcg(b + k0 + t) : 0.0;
@@ -729,6 +735,8 @@ extern "C" int lsk_potrs_upper(const void* U_, long long n, long long lda, const
     int dev = 0, sms = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    static const int cap = [] { const char* v = getenv("LSK_SWEEP_CTAS"); return v ? atoi(v) : 0; }();   // tests: fewer CTAs than blocks
+    if (cap > 0 && cap < sms) sms = cap;
     const unsigned grid = (unsigned)(nblk < sms ? nblk : sms);
     if (which & 1) {
         if ((e = cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM)) != cudaSuccess) return (int)e;

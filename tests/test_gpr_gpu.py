@@ -376,3 +376,31 @@ def test_gp_step_against_committed_golden(name):
         pred = model(xs_flat)
     assert (pred.mean.cpu() - g["posterior_mean"]).abs().max().item() <= 1e-9 * max(1.0, g["posterior_mean"].abs().max().item())
     assert (pred.covariance_matrix.cpu() - g["posterior_cov"]).abs().max().item() <= 1e-9
+
+
+def test_pipelined_solve_with_fewer_ctas_than_blocks():
+    """`lsk_potrs_upper` hands the 128-row blocks to its CTAs by a ticket, one block per round: with three CTAs for eleven blocks
+    (LSK_SWEEP_CTAS, read once per process, hence the child process) every CTA goes through several rounds and the result is
+    bit-for-bit the one of the default launch."""
+    import os, subprocess, sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from liestationarykernels_b200.linalg import CholeskyFactor
+torch.manual_seed(3)
+n = 1337
+g = torch.randn(n, n + 9, dtype=torch.float64, device="cuda")
+a = g @ g.T / n + 0.1 * torch.eye(n, dtype=torch.float64, device="cuda")
+b = torch.randn(n, dtype=torch.float64, device="cuda")
+f = CholeskyFactor(a)
+x = f.solve(b)
+assert ((a @ x - b).abs().max() / b.abs().max()).item() < 1e-11
+print(x.cpu().numpy().tobytes().hex()[:0] + str(float(x.double().sum().item()).hex()) + " " + str(float((x * x).sum().item()).hex()))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for ctas in ("3", "0"):
+        env = dict(os.environ, LSK_SWEEP_CTAS=ctas)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(p.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
